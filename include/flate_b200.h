@@ -1,0 +1,173 @@
+/*
+ * flate_b200.h -- C ABI of libflate_b200.so, the B200-native (sm_100a CUDA)
+ * drop-in for the deflate-fast encoder / inflate decoder hot path of
+ * gmlewis/moonbit-flate.
+ *
+ * The reference has no FFI: its public surface is the MoonBit root package
+ * (pkg.generated.mbti:9-45).  A MoonBit native-backend `extern "c"` shim
+ * (moonbit_flate_b200/moonbit/) binds exactly the entry points below and
+ * re-exposes Writer::new/write/close and Reader::new/read/close on top of them;
+ * INTEGRATION.md shows the binding.  Plain pointers and sizes only; no
+ * exceptions, no C++ or torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (paths in /root/reference):
+ *   fb200_deflate_*      Writer::new + write + close, i.e. Compressor::write /
+ *                        enc_speed / close (writer.mbt:10-58, deflate.mbt:157-294),
+ *                        DeflateFast::encode (deflate-fast.mbt:123-342),
+ *                        HuffmanBitWriter::write_block_dynamic / write_block_huff /
+ *                        write_stored_header (huffman-bit-writer.mbt:474-824),
+ *                        HuffmanEncoder::generate (huffman-code.mbt:295-343)
+ *   fb200_inflate_*      Reader::new + Decompressor.read until ioeof
+ *                        (inflate.mbt:305-407), next_block / read_huffman /
+ *                        read_literal / copy_history / data_block
+ *                        (inflate.mbt:345-777), DictDecoder (dict-decoder.mbt)
+ *   fb200_writer_*       the streaming Writer object (writer.mbt:10-58)
+ *   fb200_reader_*       the streaming Decompressor object (inflate.mbt:257-418)
+ *
+ * Every stream produced by fb200_deflate_* is byte-identical to what the
+ * reference's Writer emits for the same bytes; every stream is decoded
+ * bit-exactly as the reference's Decompressor would, including its error
+ * classification and "corrupt input before offset N" offsets.
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * FB200_ERR_CUDA when no sm_100 device / driver is usable.
+ */
+#ifndef FLATE_B200_H
+#define FLATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_VERSION 1
+
+/* ---- call-level return codes ---- */
+#define FB200_OK 0
+#define FB200_ERR_ARG (-1)           /* bad argument (NULL, offsets not monotone, ...) */
+#define FB200_ERR_DST_TOO_SMALL (-2) /* output capacity insufficient; *out_len = need  */
+#define FB200_ERR_CUDA (-3)          /* CUDA runtime / launch failure, or no device    */
+#define FB200_ERR_CLOSED (-4)        /* write after close: "writer closed" (deflate.mbt:154) */
+#define FB200_ERR_NOMEM (-5)
+
+/* ---- per-stream inflate status (status[] arrays) ---- */
+#define FB200_ST_EOF 0            /* final block reached: reference err == ioeof          */
+#define FB200_ST_CORRUPT 1        /* "flate: corrupt input before offset N", N = err_off  */
+#define FB200_ST_UNEXPECTED_EOF 2 /* @io.err_unexpected_eof (inflate.mbt:781-786)         */
+#define FB200_ST_DST_TOO_SMALL 3  /* output slot too small (not a reference condition)    */
+#define FB200_ST_INTERNAL 4       /* "flate: internal error: ..."                         */
+#define FB200_ST_EOF_AT_REFILL 5  /* input ended inside more_bits (inflate.mbt:789-799):
+                                     the reference reports plain ioeof here as well        */
+
+typedef struct fb200_ctx fb200_ctx;
+
+/* One context per host thread and GPU; not thread-safe.  device < 0 selects the
+ * current CUDA device.  Owns a stream and grow-only device scratch. */
+int fb200_create(fb200_ctx **out, int device);
+void fb200_destroy(fb200_ctx *ctx);
+/* Human-readable text of the last failure on this context ("" if none). */
+const char *fb200_last_error(const fb200_ctx *ctx);
+int fb200_version(void);
+
+/* ------------------------------------------------------------------ */
+/* Sizes.                                                              */
+/* Upper bound on the compressed size of ONE stream of n bytes. */
+uint64_t fb200_deflate_stream_bound(uint64_t n);
+/* Upper bound for n bytes cut into seg_size-byte independent streams. */
+uint64_t fb200_deflate_bound(uint64_t n, uint64_t seg_size);
+
+/* ------------------------------------------------------------------ */
+/* Batch deflate, HOST buffers (copies are part of the call).          */
+/* src[0..n) is cut into ceil(n/seg_size) segments; each is compressed as an
+ * independent, complete reference stream (ends with the 5-byte final stored
+ * block, deflate.mbt:171).  Streams are laid out back to back in dst;
+ * seg_off[i] .. seg_off[i+1] delimit stream i (seg_off has nseg+1 entries). */
+int fb200_deflate_segments(fb200_ctx *ctx, const uint8_t *src, uint64_t n, uint64_t seg_size,
+                           uint8_t *dst, uint64_t dst_cap, uint64_t *seg_off, uint64_t *out_len);
+/* Same with explicit stream boundaries: stream i = src[src_off[i] .. src_off[i+1]). */
+int fb200_deflate_streams(fb200_ctx *ctx, const uint8_t *src, const uint64_t *src_off, uint64_t nstreams,
+                          uint8_t *dst, uint64_t dst_cap, uint64_t *dst_off, uint64_t *out_len);
+
+/* Batch deflate, DEVICE buffers (no host<->device payload copies; the call
+ * enqueues on the context stream and synchronises before returning).
+ * d_src_off / d_dst_off are device arrays of nstreams+1 uint64.  *out_len
+ * (host) receives the total compressed size. */
+int fb200_deflate_streams_dev(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t *d_src_off,
+                              uint64_t nstreams, uint64_t n_total, uint8_t *d_dst, uint64_t dst_cap,
+                              uint64_t *d_dst_off, uint64_t *out_len);
+/* Fixed-size segments on device; d_seg_off: device array of nseg+1 uint64. */
+int fb200_deflate_segments_dev(fb200_ctx *ctx, const uint8_t *d_src, uint64_t n, uint64_t seg_size,
+                               uint8_t *d_dst, uint64_t dst_cap, uint64_t *d_seg_off, uint64_t *out_len);
+
+/* ------------------------------------------------------------------ */
+/* Batch inflate.                                                      */
+/* Stream i = comp[comp_off[i] .. comp_off[i+1]); its output goes to
+ * out[out_off[i] .. out_off[i+1]) (a capacity slot).  out_len[i] = bytes
+ * produced (partial output before an error is kept, inflate.mbt:403-405),
+ * status[i] one of FB200_ST_*, err_off[i] = the reference's roffset for
+ * FB200_ST_CORRUPT, consumed[i] (may be NULL) = input bytes consumed. */
+int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const uint64_t *comp_off, uint64_t nstreams,
+                        uint8_t *out, const uint64_t *out_off, uint64_t *out_len, int32_t *status,
+                        int64_t *err_off, uint64_t *consumed);
+/* Device-buffer variant: every pointer is a device pointer (consumed may be NULL). */
+int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t *d_comp_off,
+                            uint64_t nstreams, uint8_t *d_out, const uint64_t *d_out_off, uint64_t *d_out_len,
+                            int32_t *d_status, int64_t *d_err_off, uint64_t *d_consumed);
+
+/* ------------------------------------------------------------------ */
+/* Multi-GPU framing helpers (one process per GPU).  The
+ * reference defines no container; this frame is an addition:
+ *   magic "FB2\0" u32 | seg_size u32 | nseg u64 | comp_size u32[nseg] | streams */
+#define FB200_FRAME_MAGIC 0x00324246u
+uint64_t fb200_frame_header_bytes(uint64_t nseg);
+
+/* ------------------------------------------------------------------ */
+/* Streaming objects mirroring the reference API (host buffers).       */
+typedef struct fb200_writer fb200_writer;
+/* sink is called with each run of compressed bytes (the &@io.Writer passed to
+ * Writer::new, writer.mbt:10); return 0 on success, non-zero = sticky I/O error. */
+typedef int (*fb200_sink_fn)(void *user, const uint8_t *data, uint64_t n);
+fb200_writer *fb200_writer_new(fb200_ctx *ctx, fb200_sink_fn sink, void *user);
+/* Writer::new_dict (writer.mbt:25-31): the dictionary is compressed into the
+ * output as if it had been written first (reference quirk, deflate_test.mbt:12-35). */
+fb200_writer *fb200_writer_new_dict(fb200_ctx *ctx, fb200_sink_fn sink, void *user, const uint8_t *dict,
+                                    uint64_t n);
+/* impl @io.Writer for Writer (writer.mbt:45): returns bytes accepted (== n) or a
+ * negative FB200_ERR_* (FB200_ERR_CLOSED after close). */
+int64_t fb200_writer_write(fb200_writer *w, const uint8_t *data, uint64_t n);
+/* impl @io.Closer for Writer (writer.mbt:53); a second close returns FB200_OK. */
+int fb200_writer_close(fb200_writer *w);
+void fb200_writer_free(fb200_writer *w);
+
+typedef struct fb200_reader fb200_reader;
+/* &Reader::new (inflate.mbt:305): comp must stay valid until the first read. */
+fb200_reader *fb200_reader_new(fb200_ctx *ctx, const uint8_t *comp, uint64_t n);
+/* impl @io.Reader for Decompressor (inflate.mbt:382-407).  Returns the byte
+ * count; *status = -1 while the reference returns (n, None), otherwise the
+ * FB200_ST_* code delivered together with the last bytes. */
+uint64_t fb200_reader_read(fb200_reader *r, uint8_t *buf, uint64_t n, int32_t *status, int64_t *err_off);
+/* impl @io.Closer for Decompressor (inflate.mbt:410-415): FB200_ST_EOF* -> 0. */
+int fb200_reader_close(fb200_reader *r);
+void fb200_reader_free(fb200_reader *r);
+
+/* ------------------------------------------------------------------ */
+/* Introspection used by the parity tests and the bench (device-side
+ * intermediates of the last fb200_deflate_* call on this context).    */
+typedef struct {
+  uint64_t nblocks;      /* blocks over all streams (final empty stored block excluded) */
+  uint64_t ntokens;      /* tokens of all parsed blocks                                 */
+  uint64_t kernel_launches; /* kernels launched by the last call                        */
+} fb200_stats;
+int fb200_last_stats(const fb200_ctx *ctx, fb200_stats *out);
+/* Copy per-block results of the last deflate call to host arrays (each may be
+ * NULL): token counts, kinds (0 stored, 1 huff-only, 2 dynamic), bit sizes;
+ * tokens[] receives the concatenated token arrays (tok_cap entries max). */
+int fb200_last_blocks(const fb200_ctx *ctx, uint32_t *blk_ntok, uint8_t *blk_kind, uint32_t *blk_bits,
+                      uint64_t blk_cap, uint32_t *tokens, uint64_t tok_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,590 @@
+// api.cu -- C ABI of libflate_b200.so (include/flate_b200.h): context, device
+// scratch, kernel sequencing, host<->device staging, and the streaming
+// Writer / Decompressor objects that mirror the reference API
+// (writer.mbt:10-58, inflate.mbt:257-418).
+//
+// No CPU fallback exists: every compute entry point runs the CUDA kernels or
+// fails with FB200_ERR_CUDA.
+#include "../../include/flate_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace fb;
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      want = bytes;
+      e = cudaMalloc(&p, want);
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+} // namespace
+
+struct fb200_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // deflate scratch
+  DevBuf stream_blk0, stream_bytes, stream_trailer, dst_off_own, blk_stream, blk_ntok, blk_kind, blk_bits,
+      blk_bit_start, blk_hdr_nbits, blk_hdr, blk_freq, blk_code, tokens, counters;
+  // staging for the host-buffer entry points
+  DevBuf h_src, h_src_off, h_dst, h_dst_off;
+  DevBuf i_comp, i_comp_off, i_out, i_out_off, i_out_len, i_status, i_err_off, i_consumed;
+  uint64_t *pinned = nullptr; // small pinned read-back area
+  // last deflate job (for introspection)
+  DeflateJob last{};
+  uint64_t last_n_total = 0;
+  fb200_stats stats{};
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      char buf__[256];                                                                        \
+      snprintf(buf__, sizeof buf__, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      ctx->err = buf__;                                                                       \
+      cudaGetLastError();                                                                     \
+      return FB200_ERR_CUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+extern "C" int fb200_version(void) { return FB200_VERSION; }
+
+extern "C" int fb200_create(fb200_ctx **out, int device)
+{
+  if (!out) return FB200_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return FB200_ERR_CUDA; // no CPU fallback
+  }
+  fb200_ctx *ctx = new (std::nothrow) fb200_ctx();
+  if (!ctx) return FB200_ERR_NOMEM;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) { delete ctx; return FB200_ERR_CUDA; }
+  }
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    cudaGetLastError();
+    return FB200_ERR_CUDA;
+  }
+  if (prop.major < 10) { // built for sm_100a only
+    delete ctx;
+    return FB200_ERR_CUDA;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void **)&ctx->pinned, 64 * sizeof(uint64_t)) != cudaSuccess) {
+    delete ctx;
+    cudaGetLastError();
+    return FB200_ERR_CUDA;
+  }
+  launch_init_tables(ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    delete ctx;
+    cudaGetLastError();
+    return FB200_ERR_CUDA;
+  }
+  *out = ctx;
+  return FB200_OK;
+}
+
+extern "C" void fb200_destroy(fb200_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  DevBuf *all[] = {&ctx->stream_blk0, &ctx->stream_bytes, &ctx->stream_trailer, &ctx->dst_off_own, &ctx->blk_stream,
+                   &ctx->blk_ntok, &ctx->blk_kind, &ctx->blk_bits, &ctx->blk_bit_start, &ctx->blk_hdr_nbits,
+                   &ctx->blk_hdr, &ctx->blk_freq, &ctx->blk_code, &ctx->tokens, &ctx->counters, &ctx->h_src,
+                   &ctx->h_src_off, &ctx->h_dst, &ctx->h_dst_off, &ctx->i_comp, &ctx->i_comp_off, &ctx->i_out,
+                   &ctx->i_out_off, &ctx->i_out_len, &ctx->i_status, &ctx->i_err_off, &ctx->i_consumed};
+  for (DevBuf *b : all) b->release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *fb200_last_error(const fb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" uint64_t fb200_deflate_stream_bound(uint64_t n)
+{
+  // every code <= 15 bits per literal byte, a match token (>= 4 bytes) <= 48 bits,
+  // block header < 640 B, one block per 65535 bytes, 5-byte final block
+  const uint64_t nblk = n / kBlockSize + 1;
+  return 2 * n + 640 * nblk + 16;
+}
+
+extern "C" uint64_t fb200_deflate_bound(uint64_t n, uint64_t seg_size)
+{
+  if (seg_size == 0) return 0;
+  const uint64_t nseg = (n + seg_size - 1) / seg_size;
+  return nseg * fb200_deflate_stream_bound(seg_size < n ? seg_size : n) + 16;
+}
+
+extern "C" uint64_t fb200_frame_header_bytes(uint64_t nseg) { return 16 + 4 * nseg; }
+
+// ------------------------------------------------------------------
+// deflate core: phase A = everything up to the output layout (returns the
+// total compressed size), phase B = bit packing into d_dst.
+
+static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t *d_src_off, uint64_t ns,
+                           uint64_t n_total, uint64_t *d_dst_off, uint64_t *total_out)
+{
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ctx->stats = fb200_stats{};
+  if (ns > 0xfffffff0ull) { ctx->err = "too many streams"; return FB200_ERR_ARG; }
+  DeflateJob &j = ctx->last;
+  j = DeflateJob{};
+  j.src = d_src;
+  j.stream_off = d_src_off;
+  j.nstreams = ns;
+  CK(ctx->stream_blk0.ensure((ns + 1) * 8));
+  CK(ctx->stream_bytes.ensure((ns + 1) * 8));
+  CK(ctx->stream_trailer.ensure((ns + 1) * 8));
+  CK(ctx->counters.ensure(64));
+  j.stream_blk0 = ctx->stream_blk0.as<uint64_t>();
+  j.stream_bytes = ctx->stream_bytes.as<uint64_t>();
+  j.stream_trailer_bit = ctx->stream_trailer.as<uint64_t>();
+  j.dst_off = d_dst_off;
+  j.counters = ctx->counters.as<uint32_t>();
+  CK(cudaMemsetAsync(j.counters, 0, 64, st));
+  uint64_t launches = 0;
+
+  launch_count_blocks(j, st);
+  launch_scan_u64(j.stream_blk0, j.stream_blk0, ns, st);
+  launches += 2;
+  CK(cudaMemcpyAsync(ctx->pinned, j.stream_blk0 + ns, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t nb = ctx->pinned[0];
+  if (nb > 0x7fffffffull) { ctx->err = "too many blocks in one call"; return FB200_ERR_ARG; }
+  j.nblocks = nb;
+  const uint64_t nbp = nb + 1;
+  CK(ctx->blk_stream.ensure(nbp * 4));
+  CK(ctx->blk_ntok.ensure(nbp * 4));
+  CK(ctx->blk_kind.ensure(nbp));
+  CK(ctx->blk_bits.ensure(nbp * 4));
+  CK(ctx->blk_bit_start.ensure(nbp * 8));
+  CK(ctx->blk_hdr_nbits.ensure(nbp * 4));
+  CK(ctx->blk_hdr.ensure(nbp * kHdrWords * 4));
+  CK(ctx->blk_freq.ensure(nbp * kFreqStride * 4));
+  CK(ctx->blk_code.ensure(nbp * kFreqStride * 4));
+  CK(ctx->tokens.ensure((n_total + 16) * 4));
+  j.blk_stream = ctx->blk_stream.as<uint32_t>();
+  j.blk_ntok = ctx->blk_ntok.as<uint32_t>();
+  j.blk_kind = ctx->blk_kind.as<uint8_t>();
+  j.blk_bits = ctx->blk_bits.as<uint32_t>();
+  j.blk_bit_start = ctx->blk_bit_start.as<uint64_t>();
+  j.blk_hdr_nbits = ctx->blk_hdr_nbits.as<uint32_t>();
+  j.blk_hdr = ctx->blk_hdr.as<uint32_t>();
+  j.blk_freq = ctx->blk_freq.as<uint32_t>();
+  j.blk_code = ctx->blk_code.as<uint32_t>();
+  j.tokens = ctx->tokens.as<uint32_t>();
+  ctx->last_n_total = n_total;
+  CK(cudaMemsetAsync(j.blk_ntok, 0, nbp * 4, st));
+  CK(cudaMemsetAsync(j.blk_bits, 0, nbp * 4, st));
+
+  launch_fill_blocks(j, st);
+  launch_parse(j, ctx->num_sms, st);
+  launch_histogram(j, st);
+  launch_build_codes(j, st);
+  launch_layout(j, st);
+  launch_scan_u64(j.stream_bytes, j.dst_off, ns, st);
+  launches += 7;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->pinned, j.dst_off + ns, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *total_out = ctx->pinned[0];
+  ctx->stats.nblocks = nb;
+  ctx->stats.kernel_launches = launches;
+  return FB200_OK;
+}
+
+static int deflate_phase_b(fb200_ctx *ctx, uint8_t *d_dst, uint64_t total)
+{
+  cudaStream_t st = ctx->stream;
+  DeflateJob &j = ctx->last;
+  if ((reinterpret_cast<uintptr_t>(d_dst) & 3) != 0) { ctx->err = "device dst must be 4-byte aligned"; return FB200_ERR_ARG; }
+  j.dst = d_dst;
+  CK(cudaMemsetAsync(d_dst, 0, (total + 3) & ~3ull, st));
+  launch_pack(j, st);
+  ctx->stats.kernel_launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->pinned, j.counters, 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint32_t *c = reinterpret_cast<const uint32_t *>(ctx->pinned);
+  if (c[4] != 0) {
+    ctx->err = "internal error: packed block size differs from the computed layout";
+    return FB200_ERR_CUDA;
+  }
+  return FB200_OK;
+}
+
+extern "C" int fb200_deflate_streams_dev(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t *d_src_off,
+                                         uint64_t nstreams, uint64_t n_total, uint8_t *d_dst, uint64_t dst_cap,
+                                         uint64_t *d_dst_off, uint64_t *out_len)
+{
+  if (!ctx || !d_src_off || !d_dst_off || !out_len || (!d_src && n_total) || !d_dst) return FB200_ERR_ARG;
+  uint64_t total = 0;
+  int rc = deflate_phase_a(ctx, d_src, d_src_off, nstreams, n_total, d_dst_off, &total);
+  if (rc != FB200_OK) return rc;
+  *out_len = total;
+  if (((total + 3) & ~3ull) > dst_cap) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
+  return deflate_phase_b(ctx, d_dst, total);
+}
+
+extern "C" int fb200_deflate_segments_dev(fb200_ctx *ctx, const uint8_t *d_src, uint64_t n, uint64_t seg_size,
+                                          uint8_t *d_dst, uint64_t dst_cap, uint64_t *d_seg_off, uint64_t *out_len)
+{
+  if (!ctx || seg_size == 0 || !d_seg_off) return FB200_ERR_ARG;
+  const uint64_t nseg = (n + seg_size - 1) / seg_size;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->h_src_off.ensure((nseg + 1) * 8));
+  launch_fill_seg_off(ctx->h_src_off.as<uint64_t>(), nseg, seg_size, n, ctx->stream);
+  int rc = fb200_deflate_streams_dev(ctx, d_src, ctx->h_src_off.as<uint64_t>(), nseg, n, d_dst, dst_cap, d_seg_off,
+                                     out_len);
+  ctx->stats.kernel_launches += 1;
+  return rc;
+}
+
+static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, const uint64_t *src_off, uint64_t ns,
+                               uint64_t seg_size, uint8_t *dst, uint64_t dst_cap, uint64_t *dst_off, uint64_t *out_len)
+{
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(ctx->h_src.ensure(n + 16));
+  CK(ctx->h_src_off.ensure((ns + 1) * 8));
+  CK(ctx->h_dst_off.ensure((ns + 1) * 8));
+  if (n) CK(cudaMemcpyAsync(ctx->h_src.p, src, n, cudaMemcpyHostToDevice, st));
+  if (src_off) CK(cudaMemcpyAsync(ctx->h_src_off.p, src_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+  else launch_fill_seg_off(ctx->h_src_off.as<uint64_t>(), ns, seg_size, n, st);
+  uint64_t total = 0;
+  int rc = deflate_phase_a(ctx, ctx->h_src.as<uint8_t>(), ctx->h_src_off.as<uint64_t>(), ns, n,
+                           ctx->h_dst_off.as<uint64_t>(), &total);
+  if (rc != FB200_OK) return rc;
+  *out_len = total;
+  if (total > dst_cap) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
+  CK(ctx->h_dst.ensure(total + 16));
+  rc = deflate_phase_b(ctx, ctx->h_dst.as<uint8_t>(), total);
+  if (rc != FB200_OK) return rc;
+  CK(cudaMemcpyAsync(dst, ctx->h_dst.p, total, cudaMemcpyDeviceToHost, st));
+  if (dst_off) CK(cudaMemcpyAsync(dst_off, ctx->h_dst_off.p, (ns + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return FB200_OK;
+}
+
+extern "C" int fb200_deflate_segments(fb200_ctx *ctx, const uint8_t *src, uint64_t n, uint64_t seg_size, uint8_t *dst,
+                                      uint64_t dst_cap, uint64_t *seg_off, uint64_t *out_len)
+{
+  if (!ctx || seg_size == 0 || !out_len || (!src && n) || !dst) return FB200_ERR_ARG;
+  const uint64_t nseg = (n + seg_size - 1) / seg_size;
+  return deflate_host_common(ctx, src, n, nullptr, nseg, seg_size, dst, dst_cap, seg_off, out_len);
+}
+
+extern "C" int fb200_deflate_streams(fb200_ctx *ctx, const uint8_t *src, const uint64_t *src_off, uint64_t nstreams,
+                                     uint8_t *dst, uint64_t dst_cap, uint64_t *dst_off, uint64_t *out_len)
+{
+  if (!ctx || !src_off || !out_len || !dst) return FB200_ERR_ARG;
+  for (uint64_t i = 0; i < nstreams; i++)
+    if (src_off[i + 1] < src_off[i]) { ctx->err = "src_off not monotone"; return FB200_ERR_ARG; }
+  if (nstreams && src_off[0] != 0) { ctx->err = "src_off[0] must be 0"; return FB200_ERR_ARG; }
+  const uint64_t n = nstreams ? src_off[nstreams] : 0;
+  if (!src && n) return FB200_ERR_ARG;
+  return deflate_host_common(ctx, src, n, src_off, nstreams, 0, dst, dst_cap, dst_off, out_len);
+}
+
+extern "C" int fb200_last_stats(const fb200_ctx *ctx, fb200_stats *out)
+{
+  if (!ctx || !out) return FB200_ERR_ARG;
+  *out = ctx->stats;
+  return FB200_OK;
+}
+
+extern "C" int fb200_last_blocks(const fb200_ctx *cctx, uint32_t *blk_ntok, uint8_t *blk_kind, uint32_t *blk_bits,
+                                 uint64_t blk_cap, uint32_t *tokens, uint64_t tok_cap)
+{
+  fb200_ctx *ctx = const_cast<fb200_ctx *>(cctx);
+  if (!ctx) return FB200_ERR_ARG;
+  const DeflateJob &j = ctx->last;
+  const uint64_t nb = j.nblocks;
+  if (nb > blk_cap) return FB200_ERR_DST_TOO_SMALL;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<uint32_t> ntok(nb), stream(nb);
+  std::vector<uint64_t> blk0(j.nstreams + 1), soff(j.nstreams + 1);
+  if (nb) {
+    CK(cudaMemcpy(ntok.data(), j.blk_ntok, nb * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(stream.data(), j.blk_stream, nb * 4, cudaMemcpyDeviceToHost));
+    if (blk_ntok) memcpy(blk_ntok, ntok.data(), nb * 4);
+    if (blk_kind) CK(cudaMemcpy(blk_kind, j.blk_kind, nb, cudaMemcpyDeviceToHost));
+    if (blk_bits) CK(cudaMemcpy(blk_bits, j.blk_bits, nb * 4, cudaMemcpyDeviceToHost));
+  }
+  if (tokens) {
+    CK(cudaMemcpy(blk0.data(), j.stream_blk0, (j.nstreams + 1) * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(soff.data(), j.stream_off, (j.nstreams + 1) * 8, cudaMemcpyDeviceToHost));
+    uint64_t o = 0;
+    for (uint64_t b = 0; b < nb; b++) {
+      if (!ntok[b]) continue;
+      if (o + ntok[b] > tok_cap) return FB200_ERR_DST_TOO_SMALL;
+      const uint32_t s = stream[b];
+      const uint64_t src_off = soff[s] + (b - blk0[s]) * (uint64_t)kBlockSize;
+      CK(cudaMemcpy(tokens + o, j.tokens + src_off, (size_t)ntok[b] * 4, cudaMemcpyDeviceToHost));
+      o += ntok[b];
+    }
+  }
+  return FB200_OK;
+}
+
+// ------------------------------------------------------------------
+// inflate
+
+extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t *d_comp_off,
+                                       uint64_t nstreams, uint8_t *d_out, const uint64_t *d_out_off,
+                                       uint64_t *d_out_len, int32_t *d_status, int64_t *d_err_off,
+                                       uint64_t *d_consumed)
+{
+  if (!ctx || !d_comp_off || !d_out_off || !d_out_len || !d_status || !d_err_off) return FB200_ERR_ARG;
+  if (nstreams > 0xfffffff0ull) return FB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(ctx->counters.ensure(64));
+  CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+  InflateJob j{};
+  j.comp = d_comp;
+  j.comp_off = d_comp_off;
+  j.nstreams = nstreams;
+  j.out = d_out;
+  j.out_off = d_out_off;
+  j.out_len = d_out_len;
+  j.status = d_status;
+  j.err_off = d_err_off;
+  j.consumed = d_consumed;
+  j.counters = ctx->counters.as<uint32_t>();
+  launch_inflate(j, ctx->num_sms, st);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  ctx->stats = fb200_stats{};
+  ctx->stats.kernel_launches = nstreams ? 1 : 0;
+  return FB200_OK;
+}
+
+extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const uint64_t *comp_off, uint64_t nstreams,
+                                   uint8_t *out, const uint64_t *out_off, uint64_t *out_len, int32_t *status,
+                                   int64_t *err_off, uint64_t *consumed)
+{
+  if (!ctx || !comp_off || !out_off || !out_len || !status || !err_off) return FB200_ERR_ARG;
+  for (uint64_t i = 0; i < nstreams; i++)
+    if (comp_off[i + 1] < comp_off[i] || out_off[i + 1] < out_off[i]) { ctx->err = "offsets not monotone"; return FB200_ERR_ARG; }
+  const uint64_t nc = nstreams ? comp_off[nstreams] : 0;
+  const uint64_t no = nstreams ? out_off[nstreams] : 0;
+  if ((!comp && nc) || (!out && no)) return FB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(ctx->i_comp.ensure(nc + 16));
+  CK(ctx->i_comp_off.ensure((nstreams + 1) * 8));
+  CK(ctx->i_out.ensure(no + 16));
+  CK(ctx->i_out_off.ensure((nstreams + 1) * 8));
+  CK(ctx->i_out_len.ensure((nstreams + 1) * 8));
+  CK(ctx->i_status.ensure((nstreams + 1) * 4));
+  CK(ctx->i_err_off.ensure((nstreams + 1) * 8));
+  CK(ctx->i_consumed.ensure((nstreams + 1) * 8));
+  if (nc) CK(cudaMemcpyAsync(ctx->i_comp.p, comp, nc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->i_comp_off.p, comp_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->i_out_off.p, out_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, st));
+  int rc = fb200_inflate_batch_dev(ctx, ctx->i_comp.as<uint8_t>(), ctx->i_comp_off.as<uint64_t>(), nstreams,
+                                   ctx->i_out.as<uint8_t>(), ctx->i_out_off.as<uint64_t>(),
+                                   ctx->i_out_len.as<uint64_t>(), ctx->i_status.as<int32_t>(),
+                                   ctx->i_err_off.as<int64_t>(), ctx->i_consumed.as<uint64_t>());
+  if (rc != FB200_OK) return rc;
+  if (no) CK(cudaMemcpyAsync(out, ctx->i_out.p, no, cudaMemcpyDeviceToHost, st));
+  if (nstreams) {
+    CK(cudaMemcpyAsync(out_len, ctx->i_out_len.p, nstreams * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, ctx->i_status.p, nstreams * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(err_off, ctx->i_err_off.p, nstreams * 8, cudaMemcpyDeviceToHost, st));
+    if (consumed) CK(cudaMemcpyAsync(consumed, ctx->i_consumed.p, nstreams * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return FB200_OK;
+}
+
+// ------------------------------------------------------------------
+// Streaming Writer (writer.mbt:10-58 / deflate.mbt:157-183, :280-294).
+// The compressed bytes are a pure function of the concatenated input (blocks
+// are cut only when the 65535-byte window fills or at close), so the object
+// buffers writes and runs the GPU path at close.
+
+struct fb200_writer {
+  fb200_ctx *ctx;
+  fb200_sink_fn sink;
+  void *user;
+  std::vector<uint8_t> buf;
+  bool closed = false;
+  int sticky = 0;
+};
+
+extern "C" fb200_writer *fb200_writer_new(fb200_ctx *ctx, fb200_sink_fn sink, void *user)
+{
+  if (!ctx || !sink) return nullptr;
+  fb200_writer *w = new (std::nothrow) fb200_writer();
+  if (!w) return nullptr;
+  w->ctx = ctx;
+  w->sink = sink;
+  w->user = user;
+  return w;
+}
+
+extern "C" fb200_writer *fb200_writer_new_dict(fb200_ctx *ctx, fb200_sink_fn sink, void *user, const uint8_t *dict,
+                                               uint64_t n)
+{
+  fb200_writer *w = fb200_writer_new(ctx, sink, user);
+  if (!w) return nullptr;
+  // fill_window keeps the last 32768 bytes of the dictionary in the input window (deflate.mbt:114-120)
+  if (n > (uint64_t)kMaxMatchOffset) {
+    dict += n - kMaxMatchOffset;
+    n = kMaxMatchOffset;
+  }
+  w->buf.assign(dict, dict + n);
+  return w;
+}
+
+extern "C" int64_t fb200_writer_write(fb200_writer *w, const uint8_t *data, uint64_t n)
+{
+  if (!w) return FB200_ERR_ARG;
+  if (w->closed) return FB200_ERR_CLOSED; // writer_closed_error (deflate.mbt:154, :281-283)
+  if (w->sticky) return w->sticky;
+  if (n) w->buf.insert(w->buf.end(), data, data + n);
+  return (int64_t)n;
+}
+
+extern "C" int fb200_writer_close(fb200_writer *w)
+{
+  if (!w) return FB200_ERR_ARG;
+  if (w->closed) return FB200_OK; // deflate.mbt:158-160
+  if (w->sticky) return w->sticky;
+  const uint64_t n = w->buf.size();
+  std::vector<uint8_t> out(fb200_deflate_stream_bound(n));
+  uint64_t off[2] = {0, n}, doff[2], olen = 0;
+  int rc = fb200_deflate_streams(w->ctx, w->buf.data(), off, 1, out.data(), out.size(), doff, &olen);
+  if (rc != FB200_OK) { w->sticky = rc; return rc; }
+  if (w->sink(w->user, out.data(), olen) != 0) { w->sticky = FB200_ERR_ARG; return w->sticky; }
+  w->closed = true;
+  std::vector<uint8_t>().swap(w->buf);
+  return FB200_OK;
+}
+
+extern "C" void fb200_writer_free(fb200_writer *w) { delete w; }
+
+// Streaming Decompressor (inflate.mbt:257-418).  The first read inflates the
+// whole stream on the GPU; reads then hand the result out with the
+// reference's granularity: one 32 KiB window flush at a time, the final
+// status riding on the read that drains the last (partial) flush.
+struct fb200_reader {
+  fb200_ctx *ctx;
+  const uint8_t *comp;
+  uint64_t n;
+  bool decoded = false;
+  std::vector<uint8_t> out;
+  uint64_t total = 0, pos = 0;
+  int32_t status = -1;
+  int64_t err_off = 0;
+  int rc = FB200_OK;
+};
+
+extern "C" fb200_reader *fb200_reader_new(fb200_ctx *ctx, const uint8_t *comp, uint64_t n)
+{
+  if (!ctx || (!comp && n)) return nullptr;
+  fb200_reader *r = new (std::nothrow) fb200_reader();
+  if (!r) return nullptr;
+  r->ctx = ctx;
+  r->comp = comp;
+  r->n = n;
+  return r;
+}
+
+static void reader_decode(fb200_reader *r)
+{
+  r->decoded = true;
+  uint64_t cap = r->n * 8 + 65536;
+  for (;;) {
+    r->out.resize(cap);
+    uint64_t coff[2] = {0, r->n}, ooff[2] = {0, cap}, olen = 0, cons = 0;
+    int32_t st = -1;
+    int64_t eo = 0;
+    r->rc = fb200_inflate_batch(r->ctx, r->comp, coff, 1, r->out.data(), ooff, &olen, &st, &eo, &cons);
+    if (r->rc != FB200_OK) { r->status = FB200_ST_INTERNAL; r->total = 0; return; }
+    if (st == FB200_ST_DST_TOO_SMALL && cap < r->n * 1040 + 65536) { cap *= 4; continue; }
+    r->total = olen;
+    r->status = st;
+    r->err_off = eo;
+    return;
+  }
+}
+
+extern "C" uint64_t fb200_reader_read(fb200_reader *r, uint8_t *buf, uint64_t n, int32_t *status, int64_t *err_off)
+{
+  if (!r || !status) return 0;
+  if (!r->decoded) reader_decode(r);
+  if (r->pos == r->total) { // nothing buffered: the sticky error (inflate.mbt:398-401)
+    *status = r->status;
+    if (err_off) *err_off = r->err_off;
+    return 0;
+  }
+  const uint64_t window = (uint64_t)kMaxMatchOffset;
+  uint64_t chunk_end = (r->pos / window + 1) * window;
+  if (chunk_end > r->total) chunk_end = r->total;
+  uint64_t k = chunk_end - r->pos;
+  if (k > n) k = n;
+  memcpy(buf, r->out.data() + r->pos, k);
+  r->pos += k;
+  *status = -1;
+  // the status rides on the read that drains the final, partial window flush (inflate.mbt:392-396)
+  if (r->pos == r->total && (r->total % window) != 0) {
+    *status = r->status;
+    if (err_off) *err_off = r->err_off;
+  }
+  return k;
+}
+
+extern "C" int fb200_reader_close(fb200_reader *r)
+{
+  if (!r) return FB200_ERR_ARG;
+  if (!r->decoded) return FB200_OK; // err is still None
+  if (r->status == FB200_ST_EOF || r->status == FB200_ST_EOF_AT_REFILL || r->status < 0) return FB200_OK;
+  return r->status;
+}
+
+extern "C" void fb200_reader_free(fb200_reader *r) { delete r; }

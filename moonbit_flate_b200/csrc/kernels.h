@@ -1,0 +1,77 @@
+// kernels.h -- host-side launch interface of the CUDA kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fb {
+
+// Everything the deflate kernels need; all pointers are device pointers.
+// Streams are the independent units: stream i is
+// src[stream_off[i] .. stream_off[i+1]) and is cut into blocks of <= 65535
+// bytes exactly as Compressor::write / enc_speed does (deflate.mbt:222-294).
+struct DeflateJob {
+  const uint8_t *src;
+  const uint64_t *stream_off; // [nstreams+1]
+  uint64_t nstreams;
+  uint64_t nblocks;           // total over streams (host copy of stream_blk0[nstreams])
+  // per stream
+  uint64_t *stream_blk0;      // [nstreams+1] first block index (exclusive scan)
+  uint64_t *stream_bytes;     // [nstreams]   compressed size
+  uint64_t *stream_trailer_bit; // [nstreams] stream-relative bit offset of the final stored header
+  uint64_t *dst_off;          // [nstreams+1] output byte offsets (exclusive scan of stream_bytes)
+  // per block
+  uint32_t *blk_stream;       // [nblocks] owning stream
+  uint32_t *blk_ntok;         // [nblocks] tokens emitted by the parse (0 if not parsed)
+  uint8_t *blk_kind;          // [nblocks] kKind*
+  uint32_t *blk_bits;         // [nblocks] bits of header+data+EOB (huff/dynamic kinds)
+  uint64_t *blk_bit_start;    // [nblocks] stream-relative start bit
+  uint32_t *blk_hdr_nbits;    // [nblocks]
+  uint32_t *blk_hdr;          // [nblocks][kHdrWords] header bit string, LSB first
+  uint32_t *blk_freq;         // [nblocks][320] lit/len (286) + offset (30) histograms (+pad)
+  uint32_t *blk_code;         // [nblocks][320] code | len<<16 for lit/len (286) + offset (30)
+  // tokens of the block starting at source byte o live at tokens[o .. o+ntok)
+  uint32_t *tokens;           // [n_total]
+  uint32_t *counters;         // [8] work-stealing counters, zeroed per call
+  // output
+  uint8_t *dst;
+};
+constexpr int kFreqStride = 320;
+
+// one-time device tables (probe schedule); call once per context
+void launch_init_tables(cudaStream_t st);
+// setup: per-stream block counts -> stream_blk0 (scan) ; then per-block stream ids
+void launch_count_blocks(const DeflateJob &j, cudaStream_t st);
+void launch_fill_blocks(const DeflateJob &j, cudaStream_t st);
+// K1: greedy LZ77 parse, one warp per stream (deflate-fast.mbt:123-342)
+void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st);
+// K2: block kind + histograms (huffman-bit-writer.mbt:550-593, :831)
+void launch_histogram(const DeflateJob &j, cudaStream_t st);
+// K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,
+//     huffman-bit-writer.mbt:241-471)
+void launch_build_codes(const DeflateJob &j, cudaStream_t st);
+// layout: per-stream bit offsets, stream sizes, output offsets
+void launch_layout(const DeflateJob &j, cudaStream_t st);
+// K4: bit packing (huffman-bit-writer.mbt:596-824, :474-487) + stream trailers
+void launch_pack(const DeflateJob &j, cudaStream_t st);
+
+// exclusive scan of n uint64 values (out may alias in); out has n+1 entries
+void launch_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n, cudaStream_t st);
+// fixed-size segment offsets: off[i] = min(i*seg, n), i in [0, nseg]
+void launch_fill_seg_off(uint64_t *off, uint64_t nseg, uint64_t seg, uint64_t n, cudaStream_t st);
+
+struct InflateJob {
+  const uint8_t *comp;
+  const uint64_t *comp_off; // [nstreams+1]
+  uint64_t nstreams;
+  uint8_t *out;
+  const uint64_t *out_off;  // [nstreams+1] capacity slots
+  uint64_t *out_len;        // [nstreams]
+  int32_t *status;          // [nstreams]
+  int64_t *err_off;         // [nstreams]
+  uint64_t *consumed;       // [nstreams] or null
+  uint32_t *counters;
+};
+// K6: batched inflate, one warp per stream (inflate.mbt, dict-decoder.mbt)
+void launch_inflate(const InflateJob &j, int num_sms, cudaStream_t st);
+
+} // namespace fb

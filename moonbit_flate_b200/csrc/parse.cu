@@ -1,0 +1,318 @@
+// parse.cu -- K1: exact greedy LZ77 parse of DeflateFast::encode
+// (deflate-fast.mbt:123-342), one warp per independent stream.
+//
+// The reference walks one position at a time: probe the 1<<14-entry hash table,
+// insert the current position, test the candidate, on a hit extend the match,
+// then insert s-1 / probe s (deflate-fast.mbt:246-265).  The token sequence is
+// a pure function of the bytes, so it can be reproduced 32 probes at a time:
+//
+//  * After a match (or at block start) the probe positions are a fixed
+//    schedule: probe k of a probe loop sits at p0 + d_k with d_0 = 0,
+//    d_{k+1} = d_k + 1 + (d_k >> 5)  (skip = 32 + d_k, step = skip >> 5,
+//    deflate-fast.mbt:178-187).  Lane l of a batch takes probe k0 + l.
+//  * A "post-match" batch folds the reference's insert(s-1) and probe(s) into
+//    lanes 0 and 1 and starts the new probe loop at lane 2.
+//  * All lanes read their bucket, then same-bucket dependencies inside the
+//    batch are resolved with __match_any_sync: a lane's candidate is the
+//    nearest lower lane with the same bucket, else the old table entry --
+//    exactly what sequential execution would have read.
+//  * __ballot_sync finds the first lane that hits (distance <= 32768 and the
+//    four bytes equal, :195-196) or runs past s_limit (:188); lanes up to and
+//    including a hit lane commit their insert (the reference writes the table
+//    before testing, :191-193), the highest committed lane per bucket wins.
+//  * match_len (:286-342) compares 32 bytes per step with ballot/ffs.  A
+//    candidate in the previous block yields length 0 beyond the 4 hashed
+//    bytes because the reference never populates `prev` (quirk D1).
+//
+// The table lives in shared memory and stores positions only: `val` of the
+// reference's TableEntry is by construction load32(src, position), so it is
+// re-read from the source (L1/L2 resident).  Streams with a single parsed
+// block use uint16 positions (32 KiB per warp); longer streams, whose table
+// persists across blocks, use uint32 absolute positions + 1 (0 = empty).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cstdlib>
+#include <type_traits>
+
+namespace fb {
+
+constexpr int kSchedLen = 512;
+__device__ uint32_t g_sched[kSchedLen];
+
+__global__ void k_init_sched()
+{
+  uint32_t d = 0;
+  for (int k = 0; k < kSchedLen; k++) {
+    g_sched[k] = d;
+    d = d + 1 + (d >> 5);
+    if (d > (1u << 20)) d = 1u << 20;
+  }
+}
+
+constexpr unsigned kFull = 0xffffffffu;
+
+template <bool MULTI>
+__global__ void k_parse(DeflateJob j, uint32_t *counter)
+{
+  using T = typename std::conditional<MULTI, uint32_t, uint16_t>::type;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  T *table = reinterpret_cast<T *>(smem_raw) + (size_t)warp * kTableSize;
+  const unsigned lt_mask = (1u << lane) - 1;
+  const unsigned gt_mask = ~((2u << lane) - 1); // lanes above this one (0 for lane 31)
+
+  for (;;) {
+    uint32_t st32 = 0;
+    if (lane == 0) st32 = atomicAdd(counter, 1u);
+    st32 = __shfl_sync(kFull, st32, 0);
+    if (st32 >= j.nstreams) break;
+    const uint64_t o0 = j.stream_off[st32];
+    const uint64_t L = j.stream_off[st32 + 1] - o0;
+    const bool is_multi = L >= (uint64_t)kBlockSize + 128;
+    if (is_multi != MULTI || L < 128) continue;
+
+    // DeflateFast::new (:111-117): empty table
+    {
+      const uint32_t fill = MULTI ? 0u : 0xffffffffu;
+      uint4 *t4 = reinterpret_cast<uint4 *>(table);
+      const int n4 = (int)(kTableSize * sizeof(T) / 16);
+      for (int i = lane; i < n4; i += 32) t4[i] = make_uint4(fill, fill, fill, fill);
+      __syncwarp();
+    }
+
+    const uint64_t blk0 = j.stream_blk0[st32];
+    const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
+    for (uint32_t b = 0; b < nblk; b++) {
+      const uint64_t boff = (uint64_t)b * kBlockSize;
+      const int n = (int)((L - boff) < (uint64_t)kBlockSize ? (L - boff) : (uint64_t)kBlockSize);
+      if (n < 128) break; // small tail: not parsed (deflate.mbt:244-257)
+      const uint8_t *srcb = j.src + o0 + boff;
+      uint32_t *tok = j.tokens + o0 + boff;
+      const uint32_t S0 = (uint32_t)boff; // stream-relative block start (MULTI)
+      const int s_limit = n - kInputMargin;
+
+      int s = 0, next_emit = 0;
+      uint32_t ntok = 0;
+      bool modeM = false;
+      int loop_p0 = 0, k0 = 0;
+
+      for (;;) {
+        // ---- lane's table operation in this batch ----
+        int pos, step;
+        bool probe, loopprobe;
+        if (modeM) {
+          if (lane == 0) { // insert(s-1), :246-251
+            pos = s - 1; step = 0; probe = false; loopprobe = false;
+          } else if (lane == 1) { // probe(s), :252-260
+            pos = s; step = 0; probe = true; loopprobe = false;
+          } else { // new probe loop from s+1 with skip = 32, :261-265 -> :178-202
+            pos = s + 1 + (lane - 2); step = 1; probe = true; loopprobe = true;
+          }
+        } else {
+          const int k = k0 + lane;
+          const uint32_t d = k < 32 ? (uint32_t)k : (k < kSchedLen ? g_sched[k] : (1u << 20));
+          pos = loop_p0 + (int)d;
+          step = 1 + (int)(d >> 5);
+          probe = true; loopprobe = true;
+        }
+        const bool fail = loopprobe && (pos + step > s_limit); // :188
+        const bool active = !fail;
+
+        uint32_t cv = 0, h = 0x10000u | (uint32_t)lane;
+        T old = 0;
+        if (active) {
+          cv = ld32u(srcb + pos);
+          h = hash4(cv);
+          old = table[h];
+        }
+        const unsigned peers = __match_any_sync(kFull, h);
+        const unsigned lower = peers & lt_mask;
+        const int srcl = lower ? 31 - __clz(lower) : lane;
+        const int ppos = __shfl_sync(kFull, pos, srcl);
+        int cand;
+        bool ok;
+        if (lower) {
+          cand = ppos;
+          ok = (pos - cand) <= kMaxMatchOffset;
+        } else if (MULTI) {
+          const uint32_t D = (S0 + (uint32_t)pos + 1u) - (uint32_t)old;
+          ok = (old != 0) && (D <= (uint32_t)kMaxMatchOffset);
+          cand = pos - (int)D;
+        } else {
+          const int D = pos - (int)old;
+          ok = (D >= 1) && (D <= kMaxMatchOffset);
+          cand = (int)old;
+        }
+        bool hit = false;
+        if (active && probe && ok) hit = (ld32u(srcb + cand) == cv); // :196
+        const unsigned hitm = __ballot_sync(kFull, hit);
+        const unsigned evt = hitm | __ballot_sync(kFull, fail);
+        const int m = evt ? __ffs(evt) - 1 : 32;
+        const bool mhit = evt && ((hitm >> m) & 1u);
+        const unsigned cmask = (m == 32) ? kFull : (mhit ? ((2u << m) - 1u) : ((1u << m) - 1u));
+        const bool committed = active && ((cmask >> lane) & 1u);
+        const unsigned cm = __ballot_sync(kFull, committed);
+        if (committed && (peers & cm & gt_mask) == 0) // last writer of this bucket in program order
+          table[h] = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
+        __syncwarp();
+
+        if (m == 32) { // 32 misses: keep probing (:198-199)
+          if (modeM) { modeM = false; loop_p0 = s + 1; k0 = 30; }
+          else k0 += 32;
+          continue;
+        }
+        if (!mhit) break; // next_s > s_limit -> emit_remainder (:189)
+
+        const int s_hit = __shfl_sync(kFull, pos, m);
+        const int c = __shfl_sync(kFull, cand, m);
+        // emit_literal(src[next_emit:s]) (:207)
+        for (int i = next_emit + lane; i < s_hit; i += 32) tok[ntok + (uint32_t)(i - next_emit)] = __ldg(srcb + i);
+        ntok += (uint32_t)(s_hit - next_emit);
+        // match_len (:286-307); t < 0 -> 0 (D1, :310-313)
+        const int s2 = s_hit + 4, t = c + 4;
+        int ext = 0;
+        if (t >= 0) {
+          int s1 = s2 + kMaxMatchLength - 4;
+          if (s1 > n) s1 = n;
+          const int a = s1 - s2;
+          ext = a;
+          for (int base = 0; base < a; base += 32) {
+            const int i = base + lane;
+            const bool mism = (i >= a) || (__ldg(srcb + s2 + i) != __ldg(srcb + t + i));
+            const unsigned mm = __ballot_sync(kFull, mism);
+            if (mm) { ext = base + __ffs(mm) - 1; break; }
+          }
+        }
+        if (lane == 0) // match_token(l + 4 - 3, s - t - 1) (:228-233)
+          tok[ntok] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1);
+        ntok++;
+        s = s2 + ext;
+        next_emit = s;
+        if (s >= s_limit) break; // :236-238
+        modeM = true;
+      }
+      // emit_remainder (:152-159)
+      for (int i = next_emit + lane; i < n; i += 32) tok[ntok + (uint32_t)(i - next_emit)] = __ldg(srcb + i);
+      ntok += (uint32_t)(n - next_emit);
+      if (lane == 0) j.blk_ntok[blk0 + b] = ntok;
+      __syncwarp();
+    }
+  }
+}
+
+void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
+
+static int g_parse_occ_single = 0, g_parse_occ_multi = 0;
+
+void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
+{
+  static bool inited = false;
+  if (!inited) {
+    const char *e = getenv("FB200_PARSE_WARPS");
+    int w = e ? atoi(e) : 5;
+    if (w < 1) w = 1;
+    if (w > 7) w = 7;
+    g_parse_occ_single = w;
+    g_parse_occ_multi = w > 3 ? 3 : w;
+    cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         g_parse_occ_single * kTableSize * 2);
+    cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         g_parse_occ_multi * kTableSize * 4);
+    inited = true;
+  }
+  k_parse<false><<<num_sms, g_parse_occ_single * 32, g_parse_occ_single * kTableSize * 2, st>>>(j, j.counters + 0);
+  k_parse<true><<<num_sms, g_parse_occ_multi * 32, g_parse_occ_multi * kTableSize * 4, st>>>(j, j.counters + 1);
+}
+
+// ------------------------------------------------------------------
+// setup kernels
+
+__global__ void k_count_blocks(DeflateJob j, uint64_t *nblk_out)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.nstreams) return;
+  uint64_t L = j.stream_off[i + 1] - j.stream_off[i];
+  nblk_out[i] = (L + kBlockSize - 1) / kBlockSize; // Compressor::write cuts at 65535 (deflate.mbt:222-229,:238)
+}
+
+void launch_count_blocks(const DeflateJob &j, cudaStream_t st)
+{
+  if (j.nstreams == 0) return;
+  unsigned g = (unsigned)((j.nstreams + 255) / 256);
+  k_count_blocks<<<g, 256, 0, st>>>(j, j.stream_blk0);
+}
+
+__global__ void k_fill_blocks(DeflateJob j)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.nstreams) return;
+  uint64_t b0 = j.stream_blk0[i], b1 = j.stream_blk0[i + 1];
+  for (uint64_t b = b0; b < b1; b++) j.blk_stream[b] = (uint32_t)i;
+}
+
+void launch_fill_blocks(const DeflateJob &j, cudaStream_t st)
+{
+  if (j.nstreams == 0) return;
+  unsigned g = (unsigned)((j.nstreams + 255) / 256);
+  k_fill_blocks<<<g, 256, 0, st>>>(j);
+}
+
+__global__ void k_fill_seg_off(uint64_t *off, uint64_t nseg, uint64_t seg, uint64_t n)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nseg) return;
+  uint64_t v = i * seg;
+  off[i] = v < n ? v : n;
+}
+
+void launch_fill_seg_off(uint64_t *off, uint64_t nseg, uint64_t seg, uint64_t n, cudaStream_t st)
+{
+  unsigned g = (unsigned)((nseg + 1 + 255) / 256);
+  k_fill_seg_off<<<g, 256, 0, st>>>(off, nseg, seg, n);
+}
+
+// Single-CTA exclusive scan (metadata only: <= a few million entries).
+__global__ void __launch_bounds__(1024) k_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n)
+{
+  __shared__ uint64_t wsum[32];
+  __shared__ uint64_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < n; base += 1024) {
+    uint64_t i = base + tid;
+    uint64_t v = i < n ? in[i] : 0;
+    uint64_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t y = __shfl_up_sync(kFull, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t w = wsum[lane];
+      uint64_t xs = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(kFull, xs, o);
+        if (lane >= o) xs += y;
+      }
+      wsum[lane] = xs - w; // exclusive
+    }
+    __syncthreads();
+    const uint64_t carry = carry_s;
+    if (i < n) out[i] = carry + wsum[warp] + x - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[31] + x;
+    __syncthreads();
+  }
+  if (tid == 0) out[n] = carry_s;
+}
+
+void launch_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n, cudaStream_t st)
+{
+  k_scan_u64<<<1, 1024, 0, st>>>(in, out, n);
+}
+
+} // namespace fb

@@ -1,0 +1,168 @@
+// hostmodel.cu -- CPU-side checks of GPU kernel logic (test infrastructure).
+//
+// 1. Exposes the host compilation of the K3 building blocks
+//    (moonbit_flate_b200/csrc/huff_build.cuh: the very code k_build_codes runs
+//    per thread) so the CPU suite can diff it against the oracle.
+// 2. A lane-by-lane emulation of K1's 32-wide batched probe (parse.cu): same
+//    batch schedule, same intra-batch bucket resolution, same commit rule, run
+//    sequentially over 32 "lanes", to check the batching argument against the
+//    oracle's sequential parse without a GPU.
+#include "../../moonbit_flate_b200/csrc/common.cuh"
+#include "../../moonbit_flate_b200/csrc/huff_build.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace fb;
+
+extern "C" void fbm_generate(const uint32_t *freq, int nsym, int max_bits, uint8_t *len, uint16_t *code)
+{
+  generate_dev(freq, nsym, max_bits, len, code);
+}
+
+extern "C" int fbm_build_block(uint32_t *freq, int kind, uint32_t n, uint32_t *codeout, uint32_t *hdr_words,
+                               uint32_t *hdr_nbits, uint32_t *blk_bits)
+{
+  BlockBuild r = build_block_dev(freq, kind, n, codeout, hdr_words);
+  *hdr_nbits = r.hdr_nbits;
+  *blk_bits = r.blk_bits;
+  return r.kind;
+}
+
+extern "C" void fbm_codes(uint32_t xlen, uint32_t xoff, int *out)
+{
+  int c, nb;
+  uint32_t ex;
+  length_code_of(xlen, c, nb, ex);
+  out[0] = c; out[1] = nb; out[2] = (int)ex;
+  offset_code_of(xoff, c, nb, ex);
+  out[3] = c; out[4] = nb; out[5] = (int)ex;
+}
+
+static inline uint32_t ld32(const uint8_t *p)
+{
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return v;
+}
+
+// Emulation of k_parse<MULTI> for one stream of L bytes.  tokens_out receives
+// the concatenated tokens of all parsed blocks, blk_ntok[b] the per-block counts.
+extern "C" int64_t fbm_parse_stream(const uint8_t *src, uint64_t L, uint32_t *tokens_out, uint64_t tok_cap,
+                                    uint32_t *blk_ntok, uint64_t blk_cap)
+{
+  const bool MULTI = L >= (uint64_t)kBlockSize + 128;
+  std::vector<uint32_t> table(kTableSize, MULTI ? 0u : 0xffffu);
+  std::vector<uint32_t> sched(512);
+  {
+    uint32_t d = 0;
+    for (int k = 0; k < 512; k++) {
+      sched[k] = d;
+      d = d + 1 + (d >> 5);
+      if (d > (1u << 20)) d = 1u << 20;
+    }
+  }
+  const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < nblk; b++) {
+    if (b >= blk_cap) return -1;
+    blk_ntok[b] = 0;
+    const uint64_t boff = (uint64_t)b * kBlockSize;
+    const int n = (int)((L - boff) < (uint64_t)kBlockSize ? (L - boff) : (uint64_t)kBlockSize);
+    if (n < 128 || L < 128) continue;
+    const uint8_t *srcb = src + boff;
+    uint32_t *tok = tokens_out + total;
+    const uint32_t S0 = (uint32_t)boff;
+    const int s_limit = n - kInputMargin;
+    int s = 0, next_emit = 0;
+    uint32_t ntok = 0;
+    bool modeM = false;
+    int loop_p0 = 0, k0 = 0;
+    auto emit_lits = [&](int a, int e) {
+      for (int i = a; i < e; i++) tok[ntok++] = srcb[i];
+    };
+    if (total + (uint64_t)n > tok_cap) return -1;
+    for (;;) {
+      int pos[32], cand[32];
+      bool probe[32], fail[32], active[32], hit[32];
+      uint32_t cv[32], h[32], old[32];
+      for (int lane = 0; lane < 32; lane++) {
+        int step;
+        bool loopprobe;
+        if (modeM) {
+          if (lane == 0) { pos[lane] = s - 1; step = 0; probe[lane] = false; loopprobe = false; }
+          else if (lane == 1) { pos[lane] = s; step = 0; probe[lane] = true; loopprobe = false; }
+          else { pos[lane] = s + 1 + (lane - 2); step = 1; probe[lane] = true; loopprobe = true; }
+        } else {
+          const int k = k0 + lane;
+          const uint32_t d = k < 32 ? (uint32_t)k : (k < 512 ? sched[k] : (1u << 20));
+          pos[lane] = loop_p0 + (int)d;
+          step = 1 + (int)(d >> 5);
+          probe[lane] = true; loopprobe = true;
+        }
+        fail[lane] = loopprobe && (pos[lane] + step > s_limit);
+        active[lane] = !fail[lane];
+        cv[lane] = 0; h[lane] = 0x10000u | (uint32_t)lane; old[lane] = 0;
+        if (active[lane]) {
+          cv[lane] = ld32(srcb + pos[lane]);
+          h[lane] = hash4(cv[lane]);
+          old[lane] = table[h[lane]];
+        }
+      }
+      unsigned hitm = 0, failm = 0;
+      for (int lane = 0; lane < 32; lane++) {
+        int lower = -1;
+        for (int q = lane - 1; q >= 0; q--)
+          if (h[q] == h[lane]) { lower = q; break; }
+        bool ok;
+        if (lower >= 0) {
+          cand[lane] = pos[lower];
+          ok = (pos[lane] - cand[lane]) <= kMaxMatchOffset;
+        } else if (MULTI) {
+          const uint32_t D = (S0 + (uint32_t)pos[lane] + 1u) - old[lane];
+          ok = (old[lane] != 0) && (D <= (uint32_t)kMaxMatchOffset);
+          cand[lane] = pos[lane] - (int)D;
+        } else {
+          const int D = pos[lane] - (int)old[lane];
+          ok = (D >= 1) && (D <= kMaxMatchOffset);
+          cand[lane] = (int)old[lane];
+        }
+        hit[lane] = active[lane] && probe[lane] && ok && ld32(srcb + cand[lane]) == cv[lane];
+        if (hit[lane]) hitm |= 1u << lane;
+        if (fail[lane]) failm |= 1u << lane;
+      }
+      const unsigned evt = hitm | failm;
+      const int m = evt ? __builtin_ffs((int)evt) - 1 : 32;
+      const bool mhit = evt && ((hitm >> m) & 1u);
+      for (int lane = 0; lane < 32; lane++) { // commits in lane order == highest committed lane wins
+        const bool in = (m == 32) || (mhit ? lane <= m : lane < m);
+        if (active[lane] && in) table[h[lane]] = MULTI ? (S0 + (uint32_t)pos[lane] + 1u) : (uint32_t)(uint16_t)pos[lane];
+      }
+      if (m == 32) {
+        if (modeM) { modeM = false; loop_p0 = s + 1; k0 = 30; }
+        else k0 += 32;
+        continue;
+      }
+      if (!mhit) break;
+      const int s_hit = pos[m], c = cand[m];
+      emit_lits(next_emit, s_hit);
+      const int s2 = s_hit + 4, t = c + 4;
+      int ext = 0;
+      if (t >= 0) {
+        int s1 = s2 + kMaxMatchLength - 4;
+        if (s1 > n) s1 = n;
+        const int a = s1 - s2;
+        while (ext < a && srcb[s2 + ext] == srcb[t + ext]) ext++;
+      }
+      tok[ntok++] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1);
+      s = s2 + ext;
+      next_emit = s;
+      if (s >= s_limit) break;
+      modeM = true;
+    }
+    emit_lits(next_emit, n);
+    blk_ntok[b] = ntok;
+    total += ntok;
+  }
+  return (int64_t)total;
+}

@@ -1,0 +1,232 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs (bit-exact: integer / byte work)."""
+import zlib
+
+import numpy as np
+import pytest
+
+from helpers import BLK_DYNAMIC, Corpus, Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import moonbit_flate_b200 as fb
+
+    c = fb.Context()
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    return Corpus()
+
+
+# sizes around every threshold of Compressor::enc_speed / write (deflate.mbt:236-294)
+SIZES = [0, 1, 15, 16, 17, 100, 127, 128, 129, 300, 4096, 65534, 65535, 65536, 65537, 65551, 65552,
+         65662, 65663, 70000, 131070, 131072, 200000]
+
+
+@pytest.mark.parametrize("klass", [0, 1, 2, 3, 4, 5])
+def test_deflate_stream_bytes_and_tokens(ctx, oracle, corpus, klass):
+    """Each stream's compressed bytes (and the parse's tokens) are identical to the oracle's."""
+    datas = [corpus.unit(n, seed=3, index=i, klass=klass) for i, n in enumerate(SIZES)]
+    src = np.frombuffer(b"".join(datas), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(d) for d in datas])]).astype(np.uint64)
+    comp, doff = ctx.deflate_streams(src, off)
+    nblocks = int(ctx.last_stats().nblocks)
+    ntok, kind, bits, toks = ctx.last_blocks(nblocks, src.size + 16)
+    b = 0
+    t = 0
+    for i, d in enumerate(datas):
+        want, wtok, wntok, wkind, wbits = oracle.deflate_ex(d)
+        got = comp[int(doff[i]): int(doff[i + 1])].tobytes()
+        nb = len(wntok)
+        assert list(kind[b: b + nb]) == list(wkind), (klass, len(d))
+        # the parse runs for every block >= 128 bytes; compare tokens where both ran
+        assert list(ntok[b: b + nb]) == list(wntok), (klass, len(d))
+        k = int(wntok.sum())
+        assert np.array_equal(toks[t: t + k], wtok), (klass, len(d))
+        for q in range(nb):
+            if wkind[q] != 0:
+                assert int(bits[b + q]) == int(wbits[q]), (klass, len(d), q)
+        assert got == want, (klass, len(d))
+        assert zlib.decompress(got, -15) == d
+        b += nb
+        t += k
+    assert b == nblocks
+
+
+def test_deflate_segments_mixed(ctx, oracle, corpus):
+    """north-star unit: 65536-byte segments = block(65535) + stored(1) + trailer, each an independent stream."""
+    nseg, seg = 96, 65536
+    src = corpus.fill(nseg, seg, seed=1)
+    comp, off = ctx.deflate_segments(src, seg)
+    assert off[0] == 0 and off[-1] == comp.size
+    for i in range(nseg):
+        d = src[i * seg: (i + 1) * seg].tobytes()
+        got = comp[int(off[i]): int(off[i + 1])].tobytes()
+        assert got == oracle.deflate(d), i
+
+
+def test_deflate_ragged_last_segment(ctx, oracle, corpus):
+    src = corpus.fill(5, 65536, seed=9)[: 4 * 65536 + 777]
+    comp, off = ctx.deflate_segments(src, 65536)
+    assert len(off) == 6
+    for i in range(5):
+        d = src[i * 65536: (i + 1) * 65536].tobytes()
+        assert comp[int(off[i]): int(off[i + 1])].tobytes() == oracle.deflate(d)
+
+
+def test_deflate_empty_batch(ctx):
+    comp, off = ctx.deflate_segments(np.zeros(0, np.uint8), 65536)
+    assert comp.size == 0 and list(off) == [0]
+
+
+def test_deflate_1mib_single_stream(ctx, oracle, corpus):
+    """BASELINE config 1: one 1 MiB text stream = 16 parsed blocks (table persists, quirk D1) + 16-byte stored tail."""
+    d = corpus.unit(1 << 20, seed=1, index=0, klass=0)
+    got = ctx.deflate(d)
+    assert got == oracle.deflate(d)
+
+
+def test_inflate_reference_streams(ctx, oracle, corpus):
+    datas = [corpus.unit(n, seed=5, index=i, klass=i % 6) for i, n in enumerate(SIZES * 2)]
+    comps = [oracle.deflate(d) for d in datas]
+    comp = np.frombuffer(b"".join(comps), dtype=np.uint8)
+    coff = np.concatenate([[0], np.cumsum([len(c) for c in comps])]).astype(np.uint64)
+    ooff = np.concatenate([[0], np.cumsum([len(d) + 7 for d in datas])]).astype(np.uint64)
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, coff, ooff)
+    for i, d in enumerate(datas):
+        assert st[i] == 0, (i, st[i])
+        assert int(olen[i]) == len(d)
+        assert out[int(ooff[i]): int(ooff[i]) + len(d)].tobytes() == d
+        assert int(cons[i]) == len(comps[i])
+
+
+def test_inflate_foreign_streams(ctx, oracle, corpus):
+    """zlib-produced streams: fixed Huffman, dynamic, stored, multi-block."""
+    datas, comps = [], []
+    for i, n in enumerate([0, 1, 100, 5000, 70000, 200000]):
+        for klass in (0, 2, 3):
+            d = corpus.unit(n, seed=11, index=i, klass=klass)
+            for lvl, strat in ((0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                               (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY)):
+                co = zlib.compressobj(lvl, zlib.DEFLATED, -15, 9, strat)
+                datas.append(d)
+                comps.append(co.compress(d) + co.flush())
+    comp = np.frombuffer(b"".join(comps), dtype=np.uint8)
+    coff = np.concatenate([[0], np.cumsum([len(c) for c in comps])]).astype(np.uint64)
+    ooff = np.concatenate([[0], np.cumsum([len(d) for d in datas])]).astype(np.uint64)
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, coff, ooff)
+    for i, d in enumerate(datas):
+        ost, oout, oeo, ocons = oracle.inflate(comps[i], len(d))
+        assert (int(st[i]), int(olen[i]), int(cons[i])) == (ost, len(oout), ocons), i
+        assert out[int(ooff[i]): int(ooff[i + 1])].tobytes() == d
+
+
+def _error_cases(oracle, corpus):
+    d = corpus.unit(6000, seed=2, index=0, klass=0)
+    c = oracle.deflate(d)
+    cases = [c[:k] for k in range(0, len(c), 7)]
+    rng = np.random.default_rng(4)
+    for _ in range(300):
+        b = bytearray(c)
+        i = int(rng.integers(0, len(b)))
+        b[i] ^= 1 << int(rng.integers(0, 8))
+        cases.append(bytes(b))
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_FIXED)
+    z = co.compress(d) + co.flush()
+    cases += [z[:k] for k in range(0, len(z), 41)]
+    for _ in range(100):
+        b = bytearray(z)
+        i = int(rng.integers(0, len(b)))
+        b[i] ^= 1 << int(rng.integers(0, 8))
+        cases.append(bytes(b))
+    # reserved block type, bad stored LEN/NLEN, HLIT / HDIST out of range
+    cases += [bytes([0x07]), bytes([0x01, 0x05, 0x00, 0x00, 0x00]), bytes([0x05, 0xfe, 0xff]), bytes([0xfd, 0xff, 0x03])]
+    return cases, len(d) * 4 + 70000
+
+
+def test_inflate_error_parity(ctx, oracle, corpus):
+    """Truncated and bit-flipped streams: same status class, same `corrupt input before offset N`, same partial output."""
+    cases, cap = _error_cases(oracle, corpus)
+    comp = np.frombuffer(b"".join(cases), dtype=np.uint8)
+    coff = np.concatenate([[0], np.cumsum([len(c) for c in cases])]).astype(np.uint64)
+    ooff = (np.arange(len(cases) + 1) * cap).astype(np.uint64)
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, coff, ooff)
+    for i, c in enumerate(cases):
+        ost, oout, oeo, ocons = oracle.inflate(c, cap)
+        assert int(st[i]) == ost, (i, int(st[i]), ost)
+        assert int(olen[i]) == len(oout), (i, ost)
+        assert out[int(ooff[i]): int(ooff[i]) + len(oout)].tobytes() == oout, i
+        if ost == 1:
+            assert int(eo[i]) == oeo, (i, int(eo[i]), oeo)
+        assert int(cons[i]) == ocons, (i, ost, int(cons[i]), ocons)
+
+
+def test_roundtrip_property_large(ctx, corpus):
+    """Size-independent property at a larger size: inflate(deflate(x)) == x for 1024 mixed segments, and every
+    GPU stream inflates under zlib."""
+    nseg, seg = 1024, 65536
+    src = corpus.fill(nseg, seg, seed=21)
+    comp, off = ctx.deflate_segments(src, seg)
+    ooff = (np.arange(nseg + 1) * seg).astype(np.uint64)
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, off, ooff)
+    assert (st == 0).all() and (olen == seg).all()
+    assert np.array_equal(out, src)
+    for i in range(0, nseg, 37):
+        assert zlib.decompress(comp[int(off[i]): int(off[i + 1])].tobytes(), -15) == src[i * seg:(i + 1) * seg].tobytes()
+
+
+def test_writer_reader_mirror(ctx, oracle):
+    """TestBestSpeed restated (deflate-fast_test.mbt:14-100) through the Writer / Reader mirror."""
+    import io
+
+    import moonbit_flate_b200 as fb
+
+    abc = bytes(range(128)) * (131072 // 128)
+    cases = [[65536, 0], [65536, 1, 256], [65536, 16, 65536], [65536, 127], [65536, 128, 256], [65536, 65536, 65536]]
+    for tc in cases:
+        for first_n in (1, 65534, 65535, 65536, 65537, 131072):
+            sizes = [first_n] + tc[1:]
+            buf = io.BytesIO()
+            w = fb.Writer.new(buf, ctx)
+            want = b""
+            for n in sizes:
+                assert w.write(abc[:n]) == (n, None)
+                want += abc[:n]
+            assert w.close() is None
+            assert w.close() is None
+            assert w.write(b"x") == (0, fb.WRITER_CLOSED_ERROR)
+            comp = buf.getvalue()
+            assert comp == oracle.writer_roundtrip([abc[:n] for n in sizes])
+            got, err = fb.Reader.new(comp, ctx).read_all()
+            assert err is None and got == want
+
+
+def test_writer_dict_kat(ctx):
+    """deflate_test.mbt:12-35: 28 bytes -> exactly 38 bytes; new_dict(dict)+write(text) == write(dict)+write(text)."""
+    import io
+
+    import moonbit_flate_b200 as fb
+
+    b = io.BytesIO()
+    w = fb.Writer.new(b, ctx)
+    assert w.write(b"hello world") == (11, None)
+    assert w.write(b"hello again world") == (17, None)
+    assert w.close() is None
+    want = b.getvalue()
+    assert len(want) == 38
+    b1 = io.BytesIO()
+    w = fb.Writer.new_dict(b1, b"hello world", ctx)
+    assert w.write(b"hello again world") == (17, None)
+    assert w.close() is None
+    assert b1.getvalue() == want
