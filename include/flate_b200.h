@@ -161,6 +161,21 @@ typedef struct {
   uint64_t kernel_launches; /* kernels launched by the last call                        */
 } fb200_stats;
 int fb200_last_stats(const fb200_ctx *ctx, fb200_stats *out);
+/* The context's cudaStream_t (as void*): every kernel of this context is
+ * launched on it, so callers can bracket calls with their own CUDA events. */
+void *fb200_cuda_stream(const fb200_ctx *ctx);
+/* Device time of each pipeline stage of the last deflate / inflate call,
+ * measured with CUDA events on the context stream (milliseconds; slots below;
+ * ms must have room for FB200_NUM_STAGES floats). */
+#define FB200_STAGE_SETUP 0     /* block table: count, scan, fill           */
+#define FB200_STAGE_PARSE 1     /* K1 lz77 parse (both instantiations)      */
+#define FB200_STAGE_HISTOGRAM 2 /* K2                                       */
+#define FB200_STAGE_BUILD 3     /* K3 code construction + headers           */
+#define FB200_STAGE_LAYOUT 4    /* layout + output offset scan              */
+#define FB200_STAGE_PACK 5      /* output clear + K4 bit pack + trailers    */
+#define FB200_STAGE_INFLATE 6   /* K6                                       */
+#define FB200_NUM_STAGES 7
+int fb200_last_stage_ms(const fb200_ctx *ctx, float *ms);
 /* Copy per-block results of the last deflate call to host arrays (each may be
  * NULL): token counts, kinds (0 stored, 1 huff-only, 2 dynamic), bit sizes;
  * tokens[] receives the concatenated token arrays (tok_cap entries max). */

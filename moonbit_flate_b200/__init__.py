@@ -85,6 +85,8 @@ ABI = {
     "fb200_reader_close": (C.c_int, [C.c_void_p]),
     "fb200_reader_free": (None, [C.c_void_p]),
     "fb200_last_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "fb200_cuda_stream": (C.c_void_p, [C.c_void_p]),
+    "fb200_last_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fb200_last_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
 }
 for _name, (_res, _args) in ABI.items():
@@ -223,6 +225,16 @@ class Context:
         s = Stats()
         self._check(_lib.fb200_last_stats(self._h, C.byref(s)), "fb200_last_stats")
         return s
+
+    STAGES = ("setup", "parse", "histogram", "build", "layout", "pack", "inflate")
+
+    def last_stage_ms(self) -> dict:
+        ms = np.zeros(len(self.STAGES), np.float32)
+        self._check(_lib.fb200_last_stage_ms(self._h, _ptr(ms)), "fb200_last_stage_ms")
+        return {k: float(v) for k, v in zip(self.STAGES, ms)}
+
+    def cuda_stream(self) -> int:
+        return int(_lib.fb200_cuda_stream(self._h) or 0)
 
     def last_blocks(self, nblocks: int, tok_cap: int):
         ntok = np.zeros(nblocks, np.uint32)

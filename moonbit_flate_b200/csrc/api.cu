@@ -66,6 +66,11 @@ struct fb200_ctx {
   DeflateJob last{};
   uint64_t last_n_total = 0;
   fb200_stats stats{};
+  // stage timing: event pair per stage, on the context stream
+  cudaEvent_t ev0[FB200_NUM_STAGES] = {}, ev1[FB200_NUM_STAGES] = {};
+  bool ev_used[FB200_NUM_STAGES] = {};
+  void stage_begin(int s) { cudaEventRecord(ev0[s], stream); }
+  void stage_end(int s) { cudaEventRecord(ev1[s], stream); ev_used[s] = true; }
 };
 
 #define CK(call)                                                                              \
@@ -114,6 +119,10 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
     cudaGetLastError();
     return FB200_ERR_CUDA;
   }
+  for (int i = 0; i < FB200_NUM_STAGES; i++) {
+    cudaEventCreate(&ctx->ev0[i]);
+    cudaEventCreate(&ctx->ev1[i]);
+  }
   launch_init_tables(ctx->stream);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
     delete ctx;
@@ -135,6 +144,10 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
                    &ctx->i_out_off, &ctx->i_out_len, &ctx->i_status, &ctx->i_err_off, &ctx->i_consumed};
   for (DevBuf *b : all) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int i = 0; i < FB200_NUM_STAGES; i++) {
+    if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
+    if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
+  }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -185,7 +198,9 @@ static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
   j.counters = ctx->counters.as<uint32_t>();
   CK(cudaMemsetAsync(j.counters, 0, 64, st));
   uint64_t launches = 0;
+  for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
 
+  ctx->stage_begin(FB200_STAGE_SETUP);
   launch_count_blocks(j, st);
   launch_scan_u64(j.stream_blk0, j.stream_blk0, ns, st);
   launches += 2;
@@ -220,11 +235,20 @@ static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
   CK(cudaMemsetAsync(j.blk_bits, 0, nbp * 4, st));
 
   launch_fill_blocks(j, st);
+  ctx->stage_end(FB200_STAGE_SETUP);
+  ctx->stage_begin(FB200_STAGE_PARSE);
   launch_parse(j, ctx->num_sms, st);
+  ctx->stage_end(FB200_STAGE_PARSE);
+  ctx->stage_begin(FB200_STAGE_HISTOGRAM);
   launch_histogram(j, st);
+  ctx->stage_end(FB200_STAGE_HISTOGRAM);
+  ctx->stage_begin(FB200_STAGE_BUILD);
   launch_build_codes(j, st);
+  ctx->stage_end(FB200_STAGE_BUILD);
+  ctx->stage_begin(FB200_STAGE_LAYOUT);
   launch_layout(j, st);
   launch_scan_u64(j.stream_bytes, j.dst_off, ns, st);
+  ctx->stage_end(FB200_STAGE_LAYOUT);
   launches += 7;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->pinned, j.dst_off + ns, 8, cudaMemcpyDeviceToHost, st));
@@ -241,8 +265,10 @@ static int deflate_phase_b(fb200_ctx *ctx, uint8_t *d_dst, uint64_t total)
   DeflateJob &j = ctx->last;
   if ((reinterpret_cast<uintptr_t>(d_dst) & 3) != 0) { ctx->err = "device dst must be 4-byte aligned"; return FB200_ERR_ARG; }
   j.dst = d_dst;
+  ctx->stage_begin(FB200_STAGE_PACK);
   CK(cudaMemsetAsync(d_dst, 0, (total + 3) & ~3ull, st));
   launch_pack(j, st);
+  ctx->stage_end(FB200_STAGE_PACK);
   ctx->stats.kernel_launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->pinned, j.counters, 32, cudaMemcpyDeviceToHost, st));
@@ -335,6 +361,21 @@ extern "C" int fb200_last_stats(const fb200_ctx *ctx, fb200_stats *out)
   return FB200_OK;
 }
 
+extern "C" void *fb200_cuda_stream(const fb200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int fb200_last_stage_ms(const fb200_ctx *cctx, float *ms)
+{
+  fb200_ctx *ctx = const_cast<fb200_ctx *>(cctx);
+  if (!ctx || !ms) return FB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < FB200_NUM_STAGES; i++) {
+    ms[i] = 0.f;
+    if (ctx->ev_used[i]) CK(cudaEventElapsedTime(&ms[i], ctx->ev0[i], ctx->ev1[i]));
+  }
+  return FB200_OK;
+}
+
 extern "C" int fb200_last_blocks(const fb200_ctx *cctx, uint32_t *blk_ntok, uint8_t *blk_kind, uint32_t *blk_bits,
                                  uint64_t blk_cap, uint32_t *tokens, uint64_t tok_cap)
 {
@@ -394,7 +435,10 @@ extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, co
   j.err_off = d_err_off;
   j.consumed = d_consumed;
   j.counters = ctx->counters.as<uint32_t>();
+  for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
+  ctx->stage_begin(FB200_STAGE_INFLATE);
   launch_inflate(j, ctx->num_sms, st);
+  ctx->stage_end(FB200_STAGE_INFLATE);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
   ctx->stats = fb200_stats{};
