@@ -159,6 +159,7 @@ typedef struct {
   uint64_t nblocks;      /* blocks over all streams (final empty stored block excluded) */
   uint64_t ntokens;      /* tokens of all parsed blocks                                 */
   uint64_t kernel_launches; /* kernels launched by the last call                        */
+  uint64_t inflate_fallbacks; /* streams of the last inflate call re-decoded by the exact kernel */
 } fb200_stats;
 int fb200_last_stats(const fb200_ctx *ctx, fb200_stats *out);
 /* The context's cudaStream_t (as void*): every kernel of this context is

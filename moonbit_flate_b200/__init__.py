@@ -53,7 +53,8 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_uint64)
 
 
 class Stats(C.Structure):
-    _fields_ = [("nblocks", C.c_uint64), ("ntokens", C.c_uint64), ("kernel_launches", C.c_uint64)]
+    _fields_ = [("nblocks", C.c_uint64), ("ntokens", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("inflate_fallbacks", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/flate_b200.h declares

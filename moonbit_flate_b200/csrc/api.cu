@@ -60,7 +60,7 @@ struct fb200_ctx {
       blk_bit_start, blk_hdr_nbits, blk_hdr, blk_freq, blk_code, tokens, counters;
   // staging for the host-buffer entry points
   DevBuf h_src, h_src_off, h_dst, h_dst_off;
-  DevBuf i_comp, i_comp_off, i_out, i_out_off, i_out_len, i_status, i_err_off, i_consumed;
+  DevBuf i_comp, i_comp_off, i_out, i_out_off, i_out_len, i_status, i_err_off, i_consumed, i_fallback;
   uint64_t *pinned = nullptr; // small pinned read-back area
   // last deflate job (for introspection)
   DeflateJob last{};
@@ -141,7 +141,7 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
                    &ctx->blk_ntok, &ctx->blk_kind, &ctx->blk_bits, &ctx->blk_bit_start, &ctx->blk_hdr_nbits,
                    &ctx->blk_hdr, &ctx->blk_freq, &ctx->blk_code, &ctx->tokens, &ctx->counters, &ctx->h_src,
                    &ctx->h_src_off, &ctx->h_dst, &ctx->h_dst_off, &ctx->i_comp, &ctx->i_comp_off, &ctx->i_out,
-                   &ctx->i_out_off, &ctx->i_out_len, &ctx->i_status, &ctx->i_err_off, &ctx->i_consumed};
+                   &ctx->i_out_off, &ctx->i_out_len, &ctx->i_status, &ctx->i_err_off, &ctx->i_consumed, &ctx->i_fallback};
   for (DevBuf *b : all) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < FB200_NUM_STAGES; i++) {
@@ -423,6 +423,7 @@ extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, co
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   CK(ctx->counters.ensure(64));
+  CK(ctx->i_fallback.ensure((nstreams + 1) * 4));
   CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
   InflateJob j{};
   j.comp = d_comp;
@@ -435,14 +436,17 @@ extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, co
   j.err_off = d_err_off;
   j.consumed = d_consumed;
   j.counters = ctx->counters.as<uint32_t>();
+  j.fallback = ctx->i_fallback.as<uint32_t>();
   for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
   ctx->stage_begin(FB200_STAGE_INFLATE);
   launch_inflate(j, ctx->num_sms, st);
   ctx->stage_end(FB200_STAGE_INFLATE);
   CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->pinned, j.counters, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   ctx->stats = fb200_stats{};
-  ctx->stats.kernel_launches = nstreams ? 1 : 0;
+  ctx->stats.kernel_launches = nstreams ? 2 : 0;
+  ctx->stats.inflate_fallbacks = reinterpret_cast<const uint32_t *>(ctx->pinned)[2];
   return FB200_OK;
 }
 

@@ -193,6 +193,383 @@ __device__ __forceinline__ bool need_bits(BitReader &br, int k, int *st)
   return true;
 }
 
+
+// ------------------------------------------------------------------
+// Fast path.  Valid streams (everything a deflate encoder produced) are decoded
+// here with a lean lane-0 loop: 32-bit table entries that already carry the
+// literal byte / length base / distance base and extra-bit counts, aligned
+// word refills, no per-symbol end-of-input bookkeeping.  Anything unusual --
+// a header the reference rejects, an invalid symbol, a distance beyond the
+// output, an output slot that is too small, bits consumed past the end of the
+// input -- makes the warp put the stream on the fallback list; k_inflate then
+// re-decodes it from scratch with the reference's exact error behaviour.
+// A stream that completes here consumed only real bits and every block ended
+// in its EOB, so the reference decodes it to the same bytes with status EOF
+// and roffset = ceil(bits consumed / 8) (argument in DESIGN.md).
+
+constexpr int kFastLitBits = 10;
+constexpr int kFastDistBits = 8;
+constexpr int kFastWarps = 4;
+
+// entry: [3:0] code length (0 = not in table), [7:4] extra bits, [9:8] kind, [31:16] value
+enum { FK_LIT = 0, FK_LEN = 1, FK_EOB = 2, FK_BAD = 3 };
+
+__device__ __forceinline__ uint32_t lit_entry(int sym, int n)
+{
+  uint32_t kind, eb = 0, val;
+  if (sym < 256) { kind = FK_LIT; val = (uint32_t)sym; }
+  else if (sym == 256) { kind = FK_EOB; val = 0; }
+  else if (sym < 286) {
+    const int c = sym - 257;
+    kind = FK_LEN;
+    if (c < 8) val = 3 + c;
+    else if (c == 28) val = 258;
+    else { eb = (uint32_t)(c - 4) >> 2; val = 3 + ((4 + ((c - 4) & 3)) << eb); }
+  } else { kind = FK_BAD; val = 0; }
+  return (uint32_t)n | (eb << 4) | (kind << 8) | (val << 16);
+}
+
+__device__ __forceinline__ uint32_t dist_entry(int sym, int n)
+{
+  uint32_t kind = 0, eb = 0, val;
+  if (sym < 4) val = sym + 1;
+  else if (sym < 30) { eb = (uint32_t)(sym - 2) >> 1; val = 1 + ((2 + (sym & 1)) << eb); }
+  else { kind = FK_BAD; val = 0; }
+  return (uint32_t)n | (eb << 4) | (kind << 8) | (val << 16);
+}
+
+struct FastSmem {
+  uint32_t lit_lut[1 << kFastLitBits];
+  uint32_t dist_lut[1 << kFastDistBits];
+  uint16_t cl_lut[128];
+  uint16_t lit_sorted[288];
+  uint16_t dist_sorted[32];
+  HuffTab lit, dist;
+  uint8_t lens[288 + 32];
+  uint8_t cl_lens[32];
+};
+
+// canonical description only (counts, first codes, sorted symbols); false = reference rejects the code
+__device__ bool warp_canon(const uint8_t *lens, int nsym, uint16_t *sorted, HuffTab *tab, int *mn_out, int *mx_out)
+{
+  const int lane = lane_id();
+  int c = 0;
+  if (lane >= 1 && lane <= 15)
+    for (int i = 0; i < nsym; i++) c += (lens[i] == lane);
+  const unsigned nz = __ballot_sync(kFull, c != 0);
+  if (nz == 0) return false; // empty tree: let the exact path deal with it
+  const int mn = __ffs(nz) - 1, mx = 31 - __clz(nz);
+  int code = 0, off = 0, code_at_max = 0, my_first = 0, my_off = 0;
+  for (int L = 1; L <= 15; L++) {
+    const int cL = __shfl_sync(kFull, c, L);
+    code <<= 1;
+    if (lane == L) { my_first = code; my_off = off; }
+    code += cL;
+    off += cL;
+    if (L == mx) code_at_max = code;
+  }
+  // complete, or the single 1-bit code the reference also accepts (inflate.mbt:161); anything else: exact path
+  if (code_at_max != (1 << mx) && !(code_at_max == 1 && mx == 1)) return false;
+  if (lane < 16) {
+    tab->first[lane] = (uint16_t)my_first;
+    tab->count[lane] = (uint16_t)c;
+    tab->offs[lane] = (uint16_t)my_off;
+  }
+  if (c) {
+    int k = my_off;
+    for (int i = 0; i < nsym; i++)
+      if (lens[i] == lane) sorted[k++] = (uint16_t)i;
+  }
+  *mn_out = mn;
+  *mx_out = mx;
+  __syncwarp();
+  return true;
+}
+
+template <int KIND> // 0 lit/len, 1 dist, 2 code-length code (u16 lut: sym<<4|len)
+__device__ void warp_fill_lut(void *lut_, int lut_bits, const uint16_t *sorted, const HuffTab *tab, int mn, int mx)
+{
+  const int lane = lane_id();
+  for (int idx = lane; idx < (1 << lut_bits); idx += 32) {
+    const unsigned r = __brev((unsigned)idx);
+    uint32_t e = 0;
+    for (int L = mn; L <= lut_bits && L <= mx; L++) {
+      const unsigned d = (r >> (32 - L)) - tab->first[L];
+      if (d < tab->count[L]) {
+        const int sym = sorted[tab->offs[L] + d];
+        e = KIND == 0 ? lit_entry(sym, L) : KIND == 1 ? dist_entry(sym, L) : (uint32_t)((sym << 4) | L);
+        break;
+      }
+    }
+    if (KIND == 2) reinterpret_cast<uint16_t *>(lut_)[idx] = (uint16_t)e;
+    else reinterpret_cast<uint32_t *>(lut_)[idx] = e;
+  }
+  __syncwarp();
+}
+
+// Warp-uniform bit reader: every lane holds the same state and issues the same
+// (broadcast) loads, so the decode loop runs without divergence.  Aligned 32-bit
+// refills; bits past the end of the input read as zero.
+struct FastBits {
+  const uint32_t *w;   // next aligned word to load
+  const uint8_t *end;  // one past the last input byte
+  uint64_t bb;
+  int nb;
+  __device__ __forceinline__ void init(const uint8_t *in, uint64_t len)
+  {
+    end = in + len;
+    bb = 0; nb = 0;
+    const uint8_t *p = in;
+    while (reinterpret_cast<uintptr_t>(p) & 3) { // bytes up to the first aligned word (phantom zeros past the end)
+      if (p < end) bb |= (uint64_t)__ldg(p) << nb;
+      nb += 8;
+      p++;
+    }
+    w = reinterpret_cast<const uint32_t *>(p);
+  }
+  __device__ __forceinline__ void refill()
+  {
+    if (nb < 32) {
+      uint32_t v = 0;
+      if (reinterpret_cast<const uint8_t *>(w) < end) v = __ldg(w);
+      bb |= (uint64_t)v << nb;
+      nb += 32;
+      w++;
+    }
+  }
+  __device__ __forceinline__ uint32_t peek() const { return (uint32_t)bb; }
+  __device__ __forceinline__ void drop(int n) { bb >>= n; nb -= n; }
+  __device__ __forceinline__ uint32_t take(int n)
+  {
+    const uint32_t v = (uint32_t)bb & ((1u << n) - 1u);
+    drop(n);
+    return v;
+  }
+  // bits consumed so far, relative to `in` (phantom words included)
+  __device__ __forceinline__ int64_t consumed_bits(const uint8_t *in) const
+  {
+    return (int64_t)(reinterpret_cast<const uint8_t *>(w) - in) * 8 - nb;
+  }
+};
+
+__device__ __forceinline__ int canon_long(uint32_t bits, int from, const HuffTab *tab, const uint16_t *sorted, int *n_out)
+{
+  const unsigned r = __brev(bits);
+  for (int L = from; L <= 15; L++) {
+    const unsigned d = (r >> (32 - L)) - tab->first[L];
+    if (d < tab->count[L]) { *n_out = L; return sorted[tab->offs[L] + d]; }
+  }
+  *n_out = 0;
+  return -1;
+}
+
+__constant__ uint8_t c_code_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+__global__ void __launch_bounds__(kFastWarps * 32) k_inflate_fast(InflateJob j)
+{
+  __shared__ FastSmem smem_all[kFastWarps];
+  FastSmem &sm = smem_all[threadIdx.x >> 5];
+  const int lane = lane_id();
+
+  for (;;) {
+    uint32_t st32 = 0;
+    if (lane == 0) st32 = atomicAdd(&j.counters[0], 1u);
+    st32 = __shfl_sync(kFull, st32, 0);
+    if (st32 >= j.nstreams) break;
+
+    const uint8_t *in = j.comp + j.comp_off[st32];
+    const uint64_t in_len = j.comp_off[st32 + 1] - j.comp_off[st32];
+    uint8_t *out = j.out + j.out_off[st32];
+    const uint64_t cap64 = j.out_off[st32 + 1] - j.out_off[st32];
+    const uint32_t cap = cap64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)cap64;
+    int64_t cur_len = (int64_t)in_len; // bytes from `in` (re-based after stored blocks) to the end
+    FastBits fb;
+    fb.init(in, in_len);
+    uint32_t opos = 0;
+    bool bail = in_len > 0x0fffffffull; // keep bit counts comfortably inside 32/64-bit ranges
+    bool done = false;
+
+    while (!bail && !done) {
+      // ---- block header (all lanes, uniform) ----
+      fb.refill();
+      const int final_flag = (int)fb.take(1);
+      const int typ = (int)fb.take(2);
+      if (typ == 3) { bail = true; break; }
+
+      if (typ == 0) { // stored block
+        const int64_t p = (fb.consumed_bits(in) + 7) >> 3;
+        if (p + 4 > cur_len) { bail = true; break; }
+        const uint32_t sn = (uint32_t)__ldg(in + p) | ((uint32_t)__ldg(in + p + 1) << 8);
+        const uint32_t nn = (uint32_t)__ldg(in + p + 2) | ((uint32_t)__ldg(in + p + 3) << 8);
+        if (nn != ((~sn) & 0xffffu) || p + 4 + sn > cur_len || (uint64_t)opos + sn > cap) { bail = true; break; }
+        const uint32_t sp = (uint32_t)(p + 4);
+        for (uint32_t i = lane; i < sn; i += 32) out[opos + i] = __ldg(in + sp + i);
+        opos += sn;
+        cur_len -= (int64_t)sp + sn; // re-base the bit reader at the byte after the payload
+        in += sp + sn;
+        fb.init(in, (uint64_t)cur_len);
+        __syncwarp();
+        if (final_flag) done = true;
+        continue;
+      }
+
+      int mn1 = 0, mx1 = 0, mn2 = 0, mx2 = 0;
+      if (typ == 1) {
+        for (int i = lane; i < 288; i += 32) sm.lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+        sm.lens[288 + lane] = 5;
+        __syncwarp();
+        warp_canon(sm.lens, 288, sm.lit_sorted, &sm.lit, &mn1, &mx1);
+        warp_canon(sm.lens + 288, 32, sm.dist_sorted, &sm.dist, &mn2, &mx2);
+      } else {
+        fb.refill();
+        const int nlit = (int)fb.take(5) + 257;
+        const int ndist = (int)fb.take(5) + 1;
+        const int nclen = (int)fb.take(4) + 4;
+        if (nlit > kNumLit || ndist > kNumDist) { bail = true; break; }
+        if (lane < 19) sm.cl_lens[lane] = 0;
+        __syncwarp();
+        for (int i = 0; i < nclen; i++) {
+          fb.refill();
+          const uint32_t v = fb.take(3);
+          if (lane == 0) sm.cl_lens[c_code_order[i]] = (uint8_t)v;
+        }
+        __syncwarp();
+        int mnc = 0, mxc = 0;
+        if (!warp_canon(sm.cl_lens, 19, sm.dist_sorted, &sm.dist, &mnc, &mxc)) { bail = true; break; }
+        warp_fill_lut<2>(sm.cl_lut, 7, sm.dist_sorted, &sm.dist, mnc, mxc);
+        // code lengths: uniform decode, lane 0 writes
+        bool herr = false;
+        const int n = nlit + ndist;
+        int i = 0, prev = 0;
+        while (i < n) {
+          fb.refill();
+          const uint32_t e = sm.cl_lut[fb.peek() & 127];
+          const int len = (int)(e & 15), x = (int)(e >> 4);
+          if (len == 0) { herr = true; break; }
+          fb.drop(len);
+          if (x < 16) {
+            if (lane == 0) sm.lens[i] = (uint8_t)x;
+            prev = x;
+            i++;
+            continue;
+          }
+          int rep, b = 0;
+          if (x == 16) {
+            if (i == 0) { herr = true; break; }
+            b = prev;
+            rep = 3 + (int)fb.take(2);
+          } else if (x == 17) rep = 3 + (int)fb.take(3);
+          else rep = 11 + (int)fb.take(7);
+          if (i + rep > n) { herr = true; break; }
+          for (int k = lane; k < rep; k += 32) sm.lens[i + k] = (uint8_t)b;
+          i += rep;
+          prev = b;
+        }
+        __syncwarp();
+        if (herr) { bail = true; break; }
+        uint8_t dl = 0;
+        if (lane < ndist) dl = sm.lens[nlit + lane];
+        __syncwarp();
+        sm.lens[288 + lane] = (lane < ndist) ? dl : 0;
+        __syncwarp();
+        if (sm.lens[kEob] == 0) { bail = true; break; }
+        if (!warp_canon(sm.lens, nlit, sm.lit_sorted, &sm.lit, &mn1, &mx1)) { bail = true; break; }
+        if (!warp_canon(sm.lens + 288, ndist, sm.dist_sorted, &sm.dist, &mn2, &mx2)) { bail = true; break; }
+      }
+      warp_fill_lut<0>(sm.lit_lut, kFastLitBits, sm.lit_sorted, &sm.lit, mn1, mx1);
+      warp_fill_lut<1>(sm.dist_lut, kFastDistBits, sm.dist_sorted, &sm.dist, mn2, mx2);
+
+      // ---- symbols: uniform decode; literal k of a run parks in lane k, runs are stored coalesced ----
+      uint32_t nlit_run = 0, mylit = 0;
+      uint32_t lim = cap - opos < 32u ? cap - opos : 32u; // literals that still fit before a flush / the slot end
+      for (;;) {
+        fb.refill();
+        uint32_t e = sm.lit_lut[fb.peek() & ((1u << kFastLitBits) - 1u)];
+        if ((e & 0x30fu) == 0) goto literal_long; // not in table (len 0): long code
+      have_entry:
+        fb.drop((int)(e & 15u));
+        if ((e & 0x300u) == 0) { // literal
+          if (nlit_run == lim) { // run register file full, or the slot is
+            if (lim < 32u) { bail = true; break; }
+            out[opos + lane] = (uint8_t)mylit;
+            opos += 32;
+            nlit_run = 0;
+            lim = cap - opos < 32u ? cap - opos : 32u;
+            if (lim == 0) { bail = true; break; }
+          }
+          if ((uint32_t)lane == nlit_run) mylit = e >> 16;
+          nlit_run++;
+          continue;
+        }
+        // flush the pending literal run
+        if ((uint32_t)lane < nlit_run) out[opos + lane] = (uint8_t)mylit;
+        opos += nlit_run;
+        nlit_run = 0;
+        {
+          const uint32_t kind = (e >> 8) & 3u;
+          if (kind == FK_EOB) break;
+          if (kind == FK_BAD) { bail = true; break; }
+          const uint32_t length = (e >> 16) + fb.take((int)((e >> 4) & 15u));
+          fb.refill();
+          uint32_t d = sm.dist_lut[fb.peek() & ((1u << kFastDistBits) - 1u)];
+          if ((d & 15u) == 0) {
+            int nn;
+            const int sym = canon_long(fb.peek(), kFastDistBits + 1, &sm.dist, sm.dist_sorted, &nn);
+            if (sym < 0) { bail = true; break; }
+            d = dist_entry(sym, nn);
+          }
+          fb.drop((int)(d & 15u));
+          if ((d >> 8) & 3u) { bail = true; break; }
+          const uint32_t dist = (d >> 16) + fb.take((int)((d >> 4) & 15u));
+          if (dist > opos || (uint64_t)opos + length > cap) { bail = true; break; }
+          __syncwarp();
+          uint8_t *dp = out + opos;
+          const uint8_t *sp8 = dp - dist;
+          if (dist >= 32) {
+            for (uint32_t base = 0; base < length; base += 32) {
+              const uint32_t i = base + lane;
+              if (i < length) dp[i] = sp8[i];
+              __syncwarp();
+            }
+          } else {
+            for (uint32_t i = lane; i < length; i += 32) dp[i] = sp8[i % dist];
+            __syncwarp();
+          }
+          opos += length;
+          lim = cap - opos < 32u ? cap - opos : 32u;
+        }
+        continue;
+      literal_long: {
+          int nn;
+          const int sym = canon_long(fb.peek(), kFastLitBits + 1, &sm.lit, sm.lit_sorted, &nn);
+          if (sym < 0) { bail = true; break; }
+          e = lit_entry(sym, nn);
+          goto have_entry;
+        }
+      }
+      if (bail) break;
+      if (final_flag) done = true;
+      // bits consumed beyond the real input mean the stream is truncated: exact path
+      if (fb.consumed_bits(in) > cur_len * 8) { bail = true; break; }
+    }
+
+    if (!bail && fb.consumed_bits(in) > cur_len * 8) bail = true;
+    if (lane == 0) {
+      if (bail) {
+        const uint32_t k = atomicAdd(&j.counters[2], 1u);
+        j.fallback[k] = st32;
+      } else {
+        const int64_t cb = fb.consumed_bits(in);
+        j.out_len[st32] = opos;
+        j.status[st32] = FB200_ST_EOF;
+        j.err_off[st32] = 0;
+        if (j.consumed) j.consumed[st32] = (uint64_t)((int64_t)(in - (j.comp + j.comp_off[st32])) + ((cb + 7) >> 3));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 enum { EV_NONE = 0, EV_MATCH, EV_EOB, EV_ERR, EV_STORED, EV_TABLES, EV_FIXED };
 
 __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(InflateJob j)
@@ -202,11 +579,13 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(InflateJob j)
   const int lane = lane_id();
   const uint8_t code_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+  const uint32_t nfallback = j.counters[2];
   for (;;) {
     uint32_t st32 = 0;
-    if (lane == 0) st32 = atomicAdd(&j.counters[0], 1u);
+    if (lane == 0) st32 = atomicAdd(&j.counters[1], 1u);
     st32 = __shfl_sync(kFull, st32, 0);
-    if (st32 >= j.nstreams) break;
+    if (st32 >= nfallback) break;
+    st32 = j.fallback[st32];
 
     BitReader br;
     br.in = j.comp + j.comp_off[st32];
@@ -462,10 +841,12 @@ void launch_inflate(const InflateJob &j, int num_sms, cudaStream_t st)
     ctas_per_sm = e ? atoi(e) : 8;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  uint64_t want = (j.nstreams + kInflateWarps - 1) / kInflateWarps;
+  uint64_t want = (j.nstreams + kFastWarps - 1) / kFastWarps;
   uint64_t maxg = (uint64_t)num_sms * ctas_per_sm;
   unsigned g = (unsigned)(want < maxg ? want : maxg);
-  k_inflate<<<g, kInflateWarps * 32, 0, st>>>(j);
+  k_inflate_fast<<<g, kFastWarps * 32, 0, st>>>(j);
+  // exact re-decode of whatever the fast path put on the fallback list (usually nothing)
+  k_inflate<<<(unsigned)num_sms * 2, kInflateWarps * 32, 0, st>>>(j);
 }
 
 } // namespace fb

@@ -69,7 +69,8 @@ struct InflateJob {
   int32_t *status;          // [nstreams]
   int64_t *err_off;         // [nstreams]
   uint64_t *consumed;       // [nstreams] or null
-  uint32_t *counters;
+  uint32_t *fallback;       // [nstreams] streams the fast path hands to the exact kernel
+  uint32_t *counters;       // [0] fast work counter, [1] exact work counter, [2] fallback count
 };
 // K6: batched inflate, one warp per stream (inflate.mbt, dict-decoder.mbt)
 void launch_inflate(const InflateJob &j, int num_sms, cudaStream_t st);

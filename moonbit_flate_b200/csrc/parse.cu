@@ -99,7 +99,126 @@ __global__ void k_parse(DeflateJob j, uint32_t *counter)
       int loop_p0 = 0, k0 = 0;
 
       for (;;) {
-        // ---- lane's table operation in this batch ----
+        // ---- fast path: post-match batch, 32 consecutive positions s-1 .. s+30 ----
+        // lane 0 = insert(s-1), lane 1 = probe(s), lanes 2.. = probes s+1.. (step 1).
+        // One round evaluates every lane: its 4 bytes, bucket, old entry, the 4-byte
+        // verify and up to 8 bytes of speculative match extension.  A speculative
+        // insert + read-back finds W, the width of the lane prefix in which no two
+        // lanes share a bucket (in each sharing group exactly one lane wins the
+        // store; W = lowest losing lane).  For lanes < W the old entry is what
+        // sequential execution reads whichever earlier lanes end up inserted, so the
+        // prefix is consumed match after match from registers: literals are the low
+        // byte each lane already holds, the next probe lane is s' - base, lanes
+        // skipped by a match are simply not inserted.  (Exactness argument and CPU
+        // emulation: tests/hostmodel/hostmodel.cu, fbm_parse_stream_v2.)
+        if (modeM && s + 31 <= s_limit) {
+          const int base = s - 1;
+          const int pos = base + lane;
+          const uint32_t cv = ld32u(srcb + pos);
+          if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + pos + 256));
+          const uint32_t h = hash4(cv);
+          T *slot = table + h;
+          const T old = *slot;
+          __syncwarp();
+          const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
+          *slot = mine;
+          int cand;
+          bool ok;
+          if (MULTI) {
+            const uint32_t D = (uint32_t)mine - (uint32_t)old;
+            ok = (old != 0) && (D <= (uint32_t)kMaxMatchOffset);
+            cand = pos - (int)D;
+          } else {
+            cand = (int)old;
+            ok = (uint32_t)(pos - cand - 1) < (uint32_t)kMaxMatchOffset;
+          }
+          ok = ok && (lane != 0);
+          // 12 bytes at the candidate (own position when there is none: harmless L1 hit)
+          uint32_t c0, c1, c2;
+          {
+            const uint8_t *cp = srcb + (ok ? cand : pos);
+            const uintptr_t ca = (uintptr_t)cp;
+            const uint32_t *q = (const uint32_t *)(ca & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(ca & 3) * 8;
+            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+            c0 = __funnelshift_r(w0, w1, sh);
+            c1 = __funnelshift_r(w1, w2, sh);
+            c2 = __funnelshift_r(w2, w3, sh);
+          }
+          const uint32_t p1 = __shfl_down_sync(kFull, cv, 4); // bytes pos+4 .. pos+7   (lanes <= 27)
+          const uint32_t p2 = __shfl_down_sync(kFull, cv, 8); // bytes pos+8 .. pos+11  (lanes <= 23)
+          const bool hit = ok && (c0 == cv);
+          int avail = lane <= 23 ? 8 : (lane <= 27 ? 4 : 0);
+          int extl = 0;
+          {
+            const uint32_t x1 = c1 ^ p1, x2 = c2 ^ p2;
+            const int e1 = x1 ? ((__ffs(x1) - 1) >> 3) : 4;
+            const int e2 = x2 ? ((__ffs(x2) - 1) >> 3) : 4;
+            if (avail >= 4) extl = (e1 < 4 || avail == 4) ? e1 : 4 + e2;
+            if (cand + 4 < 0) { extl = 0; avail = 99; } // candidate in the previous block: match_len == 0 (D1)
+          }
+          __syncwarp();
+          const T rb = *slot;
+          const unsigned conf = __ballot_sync(kFull, rb != mine);
+          unsigned hitm = __ballot_sync(kFull, hit);
+          const int W = conf ? __ffs(conf) - 1 : 32;
+          // final table state is written below: restore every bucket first
+          *slot = old;
+          if (W >= 2) {
+            if (W < 32) hitm &= (1u << W) - 1u;
+            unsigned keep = 0;
+            int cur = 1;
+            bool block_done = false;
+            for (;;) {
+              const unsigned hm = hitm & ~((1u << cur) - 1u);
+              if (hm == 0) { // no further hit below W: lanes cur..W-1 are literals, probing continues at lane W
+                keep |= ((W < 32 ? (1u << W) : 0u) - 1u) & ~((1u << (cur - 1)) - 1u);
+                if (lane >= cur && lane < W) tok[ntok + (uint32_t)(lane - cur)] = cv & 0xffu;
+                ntok += (uint32_t)(W - cur);
+                next_emit = base + W;
+                modeM = false; loop_p0 = base + cur + 1; k0 = W - 1 - cur;
+                break;
+              }
+              const int m = __ffs(hm) - 1;
+              keep |= ((2u << m) - 1u) & ~((1u << (cur - 1)) - 1u);
+              if (lane >= cur && lane < m) tok[ntok + (uint32_t)(lane - cur)] = cv & 0xffu;
+              ntok += (uint32_t)(m - cur);
+              const int packed = __shfl_sync(kFull, (extl << 1) | (extl == avail ? 1 : 0), m);
+              int ext = packed >> 1;
+              const int s2 = base + m + 4;
+              if (packed & 1) { // the speculative bytes all matched: keep comparing, 32 bytes per step
+                const int t = __shfl_sync(kFull, cand, m) + 4;
+                int s1 = s2 + kMaxMatchLength - 4;
+                if (s1 > n) s1 = n;
+                const int a = s1 - s2;
+                int e = a;
+                for (int off = ext; off < a; off += 32) {
+                  const int i = off + lane;
+                  const bool mism = (i >= a) || (__ldg(srcb + s2 + i) != __ldg(srcb + t + i));
+                  const unsigned mm = __ballot_sync(kFull, mism);
+                  if (mm) { e = off + __ffs(mm) - 1; break; }
+                }
+                ext = e;
+              }
+              if (lane == m) // match_token(l + 4 - 3, s - t - 1) (:228-233)
+                tok[ntok] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(pos - cand - 1);
+              ntok++;
+              s = s2 + ext;
+              next_emit = s;
+              if (s >= s_limit) { block_done = true; break; } // :236-238
+              const int ncur = s - base;
+              if (ncur >= W) break; // next batch starts at s (still post-match mode)
+              cur = ncur;
+            }
+            __syncwarp();
+            if ((keep >> lane) & 1u) *slot = mine; // kept lanes share no bucket
+            __syncwarp();
+            if (block_done) break;
+            continue;
+          }
+          __syncwarp(); // bucket shared by lanes 0/1: resolve this batch exactly below
+        }
+        // ---- generic path: lane's table operation in this batch ----
         int pos, step;
         bool probe, loopprobe;
         if (modeM) {
@@ -211,7 +330,7 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
   static bool inited = false;
   if (!inited) {
     const char *e = getenv("FB200_PARSE_WARPS");
-    int w = e ? atoi(e) : 5;
+    int w = e ? atoi(e) : 7;
     if (w < 1) w = 1;
     if (w > 7) w = 7;
     g_parse_occ_single = w;

@@ -24,7 +24,7 @@ for r in range(reps):
     c = ctx.deflate_segments_dev(src.data_ptr(), n, SEG, dst.data_ptr(), cap, off.data_ptr())
     ms_d = ctx.last_stage_ms()
     ctx.inflate_batch_dev(dst.data_ptr(), off.data_ptr(), nseg, out.data_ptr(), ooff.data_ptr(), olen.data_ptr(), st.data_ptr(), eo.data_ptr())
-    ms_i = ctx.last_stage_ms()
-    print(f"rep {r}: C/N={c/n:.4f} " + " ".join(f"{k}={v:.3f}" for k, v in ms_d.items() if k != "inflate") + f" inflate={ms_i['inflate']:.3f}")
+    ms_i = ctx.last_stage_ms(); fbk = int(ctx.last_stats().inflate_fallbacks)
+    print(f"rep {r}: C/N={c/n:.4f} " + " ".join(f"{k}={v:.3f}" for k, v in ms_d.items() if k != "inflate") + f" inflate={ms_i['inflate']:.3f} fallbacks={fbk}")
 assert torch.equal(out, src) and int(st.abs().sum()) == 0
 print("ok")
