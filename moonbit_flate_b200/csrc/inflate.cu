@@ -211,36 +211,13 @@ constexpr int kFastLitBits = 10;
 constexpr int kFastDistBits = 8;
 constexpr int kFastWarps = 4;
 
-// entry: [3:0] code length (0 = not in table), [7:4] extra bits, [9:8] kind, [31:16] value
-enum { FK_LIT = 0, FK_LEN = 1, FK_EOB = 2, FK_BAD = 3 };
-
-__device__ __forceinline__ uint32_t lit_entry(int sym, int n)
-{
-  uint32_t kind, eb = 0, val;
-  if (sym < 256) { kind = FK_LIT; val = (uint32_t)sym; }
-  else if (sym == 256) { kind = FK_EOB; val = 0; }
-  else if (sym < 286) {
-    const int c = sym - 257;
-    kind = FK_LEN;
-    if (c < 8) val = 3 + c;
-    else if (c == 28) val = 258;
-    else { eb = (uint32_t)(c - 4) >> 2; val = 3 + ((4 + ((c - 4) & 3)) << eb); }
-  } else { kind = FK_BAD; val = 0; }
-  return (uint32_t)n | (eb << 4) | (kind << 8) | (val << 16);
-}
-
-__device__ __forceinline__ uint32_t dist_entry(int sym, int n)
-{
-  uint32_t kind = 0, eb = 0, val;
-  if (sym < 4) val = sym + 1;
-  else if (sym < 30) { eb = (uint32_t)(sym - 2) >> 1; val = 1 + ((2 + (sym & 1)) << eb); }
-  else { kind = FK_BAD; val = 0; }
-  return (uint32_t)n | (eb << 4) | (kind << 8) | (val << 16);
-}
+// Table entries are (symbol << 4) | code length, 0 = not in the table (long code
+// or invalid).  A lit/len entry is a literal iff 0 < e < (256 << 4).
+constexpr uint32_t kLitLimit = 256u << 4;
 
 struct FastSmem {
-  uint32_t lit_lut[1 << kFastLitBits];
-  uint32_t dist_lut[1 << kFastDistBits];
+  uint16_t lit_lut[1 << kFastLitBits];
+  uint16_t dist_lut[1 << kFastDistBits];
   uint16_t cl_lut[128];
   uint16_t lit_sorted[288];
   uint16_t dist_sorted[32];
@@ -249,7 +226,25 @@ struct FastSmem {
   uint8_t cl_lens[32];
 };
 
+// ceil(65536 / d): (i * r) >> 16 == i / d for i <= 258, d in [1, 31]
+__constant__ uint32_t c_recip[32] = {0,    65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554,
+                                     5958, 5462,  5042,  4682,  4370,  4096,  3856,  3641, 3450, 3277, 3121,
+                                     2979, 2850,  2731,  2622,  2521,  2428,  2341,  2260, 2185, 2115};
+// length symbol 257+c -> base | extra bits << 16 (inflate.mbt:591-615); distance symbol -> same (:656-670)
+__constant__ uint32_t c_len_tab[32] = {
+    3,           4,           5,           6,           7,           8,           9,           10,
+    11 | 1 << 16, 13 | 1 << 16, 15 | 1 << 16, 17 | 1 << 16, 19 | 2 << 16, 23 | 2 << 16, 27 | 2 << 16, 31 | 2 << 16,
+    35 | 3 << 16, 43 | 3 << 16, 51 | 3 << 16, 59 | 3 << 16, 67 | 4 << 16, 83 | 4 << 16, 99 | 4 << 16, 115 | 4 << 16,
+    131 | 5 << 16, 163 | 5 << 16, 195 | 5 << 16, 227 | 5 << 16, 258, 0, 0, 0};
+__constant__ uint32_t c_dist_tab[32] = {
+    1,            2,            3,             4,             5 | 1 << 16,    7 | 1 << 16,    9 | 2 << 16,     13 | 2 << 16,
+    17 | 3 << 16, 25 | 3 << 16, 33 | 4 << 16,  49 | 4 << 16,  65 | 5 << 16,   97 | 5 << 16,   129 | 6 << 16,   193 | 6 << 16,
+    257 | 7 << 16, 385 | 7 << 16, 513 | 8 << 16, 769 | 8 << 16, 1025 | 9 << 16, 1537 | 9 << 16, 2049 | 10 << 16, 3073 | 10 << 16,
+    4097 | 11 << 16, 6145 | 11 << 16, 8193 | 12 << 16, 12289 | 12 << 16, 16385 | 13 << 16, 24577 | 13 << 16, 0, 0};
+__constant__ uint8_t c_code_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
 // canonical description only (counts, first codes, sorted symbols); false = reference rejects the code
+// (or it is an empty tree, which the exact kernel handles)
 __device__ bool warp_canon(const uint8_t *lens, int nsym, uint16_t *sorted, HuffTab *tab, int *mn_out, int *mx_out)
 {
   const int lane = lane_id();
@@ -257,7 +252,7 @@ __device__ bool warp_canon(const uint8_t *lens, int nsym, uint16_t *sorted, Huff
   if (lane >= 1 && lane <= 15)
     for (int i = 0; i < nsym; i++) c += (lens[i] == lane);
   const unsigned nz = __ballot_sync(kFull, c != 0);
-  if (nz == 0) return false; // empty tree: let the exact path deal with it
+  if (nz == 0) return false;
   const int mn = __ffs(nz) - 1, mx = 31 - __clz(nz);
   int code = 0, off = 0, code_at_max = 0, my_first = 0, my_off = 0;
   for (int L = 1; L <= 15; L++) {
@@ -286,8 +281,7 @@ __device__ bool warp_canon(const uint8_t *lens, int nsym, uint16_t *sorted, Huff
   return true;
 }
 
-template <int KIND> // 0 lit/len, 1 dist, 2 code-length code (u16 lut: sym<<4|len)
-__device__ void warp_fill_lut(void *lut_, int lut_bits, const uint16_t *sorted, const HuffTab *tab, int mn, int mx)
+__device__ void warp_fill_lut(uint16_t *lut, int lut_bits, const uint16_t *sorted, const HuffTab *tab, int mn, int mx)
 {
   const int lane = lane_id();
   for (int idx = lane; idx < (1 << lut_bits); idx += 32) {
@@ -296,13 +290,11 @@ __device__ void warp_fill_lut(void *lut_, int lut_bits, const uint16_t *sorted, 
     for (int L = mn; L <= lut_bits && L <= mx; L++) {
       const unsigned d = (r >> (32 - L)) - tab->first[L];
       if (d < tab->count[L]) {
-        const int sym = sorted[tab->offs[L] + d];
-        e = KIND == 0 ? lit_entry(sym, L) : KIND == 1 ? dist_entry(sym, L) : (uint32_t)((sym << 4) | L);
+        e = (uint32_t)((sorted[tab->offs[L] + d] << 4) | L);
         break;
       }
     }
-    if (KIND == 2) reinterpret_cast<uint16_t *>(lut_)[idx] = (uint16_t)e;
-    else reinterpret_cast<uint32_t *>(lut_)[idx] = e;
+    lut[idx] = (uint16_t)e;
   }
   __syncwarp();
 }
@@ -352,20 +344,18 @@ struct FastBits {
   }
 };
 
-__device__ __forceinline__ int canon_long(uint32_t bits, int from, const HuffTab *tab, const uint16_t *sorted, int *n_out)
+// symbol for a code longer than the table width: (sym << 4) | len, 0 if none matches
+__device__ __forceinline__ uint32_t canon_long(uint32_t bits, int from, const HuffTab *tab, const uint16_t *sorted)
 {
   const unsigned r = __brev(bits);
   for (int L = from; L <= 15; L++) {
     const unsigned d = (r >> (32 - L)) - tab->first[L];
-    if (d < tab->count[L]) { *n_out = L; return sorted[tab->offs[L] + d]; }
+    if (d < tab->count[L]) return ((uint32_t)sorted[tab->offs[L] + d] << 4) | (uint32_t)L;
   }
-  *n_out = 0;
-  return -1;
+  return 0;
 }
 
-__constant__ uint8_t c_code_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-
-__global__ void __launch_bounds__(kFastWarps * 32) k_inflate_fast(InflateJob j)
+__global__ void __launch_bounds__(kFastWarps * 32, 10) k_inflate_fast(InflateJob j)
 {
   __shared__ FastSmem smem_all[kFastWarps];
   FastSmem &sm = smem_all[threadIdx.x >> 5];
@@ -388,6 +378,9 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_inflate_fast(InflateJob j)
     uint32_t opos = 0;
     bool bail = in_len > 0x0fffffffull; // keep bit counts comfortably inside 32/64-bit ranges
     bool done = false;
+    // deferred back-reference copy: byte loaded at one match, stored at the next (hides the L2 round trip)
+    uint8_t *pend_ptr = nullptr;
+    uint32_t pend_val = 0;
 
     while (!bail && !done) {
       // ---- block header (all lanes, uniform) ----
@@ -436,7 +429,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_inflate_fast(InflateJob j)
         __syncwarp();
         int mnc = 0, mxc = 0;
         if (!warp_canon(sm.cl_lens, 19, sm.dist_sorted, &sm.dist, &mnc, &mxc)) { bail = true; break; }
-        warp_fill_lut<2>(sm.cl_lut, 7, sm.dist_sorted, &sm.dist, mnc, mxc);
+        warp_fill_lut(sm.cl_lut, 7, sm.dist_sorted, &sm.dist, mnc, mxc);
         // code lengths: uniform decode, lane 0 writes
         bool herr = false;
         const int n = nlit + ndist;
@@ -476,77 +469,83 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_inflate_fast(InflateJob j)
         if (!warp_canon(sm.lens, nlit, sm.lit_sorted, &sm.lit, &mn1, &mx1)) { bail = true; break; }
         if (!warp_canon(sm.lens + 288, ndist, sm.dist_sorted, &sm.dist, &mn2, &mx2)) { bail = true; break; }
       }
-      warp_fill_lut<0>(sm.lit_lut, kFastLitBits, sm.lit_sorted, &sm.lit, mn1, mx1);
-      warp_fill_lut<1>(sm.dist_lut, kFastDistBits, sm.dist_sorted, &sm.dist, mn2, mx2);
+      warp_fill_lut(sm.lit_lut, kFastLitBits, sm.lit_sorted, &sm.lit, mn1, mx1);
+      warp_fill_lut(sm.dist_lut, kFastDistBits, sm.dist_sorted, &sm.dist, mn2, mx2);
 
-      // ---- symbols: uniform decode; literal k of a run parks in lane k, runs are stored coalesced ----
-      uint32_t nlit_run = 0, mylit = 0;
-      uint32_t lim = cap - opos < 32u ? cap - opos : 32u; // literals that still fit before a flush / the slot end
+      // ---- symbols: uniform decode; lane 0 stores literals, all lanes copy matches ----
       for (;;) {
-        fb.refill();
+        fb.refill(); // >= 32 bits: room for two lit/len codes
         uint32_t e = sm.lit_lut[fb.peek() & ((1u << kFastLitBits) - 1u)];
-        if ((e & 0x30fu) == 0) goto literal_long; // not in table (len 0): long code
-      have_entry:
-        fb.drop((int)(e & 15u));
-        if ((e & 0x300u) == 0) { // literal
-          if (nlit_run == lim) { // run register file full, or the slot is
-            if (lim < 32u) { bail = true; break; }
-            out[opos + lane] = (uint8_t)mylit;
-            opos += 32;
-            nlit_run = 0;
-            lim = cap - opos < 32u ? cap - opos : 32u;
-            if (lim == 0) { bail = true; break; }
+        if (e - 1u < kLitLimit - 1u) { // literal
+          if (opos >= cap) { bail = true; break; } // slot full: the exact kernel reports it
+          if (lane == 0) out[opos] = (uint8_t)(e >> 4);
+          opos++;
+          fb.drop((int)(e & 15u));
+          e = sm.lit_lut[fb.peek() & ((1u << kFastLitBits) - 1u)];
+          if (e - 1u < kLitLimit - 1u) { // second literal on the same refill
+            if (opos >= cap) { bail = true; break; }
+            if (lane == 0) out[opos] = (uint8_t)(e >> 4);
+            opos++;
+            fb.drop((int)(e & 15u));
+            continue;
           }
-          if ((uint32_t)lane == nlit_run) mylit = e >> 16;
-          nlit_run++;
-          continue;
         }
-        // flush the pending literal run
-        if ((uint32_t)lane < nlit_run) out[opos + lane] = (uint8_t)mylit;
-        opos += nlit_run;
-        nlit_run = 0;
-        {
-          const uint32_t kind = (e >> 8) & 3u;
-          if (kind == FK_EOB) break;
-          if (kind == FK_BAD) { bail = true; break; }
-          const uint32_t length = (e >> 16) + fb.take((int)((e >> 4) & 15u));
-          fb.refill();
-          uint32_t d = sm.dist_lut[fb.peek() & ((1u << kFastDistBits) - 1u)];
-          if ((d & 15u) == 0) {
-            int nn;
-            const int sym = canon_long(fb.peek(), kFastDistBits + 1, &sm.dist, sm.dist_sorted, &nn);
-            if (sym < 0) { bail = true; break; }
-            d = dist_entry(sym, nn);
+        if (e == 0) { // long code (or no code at all)
+          e = canon_long(fb.peek(), kFastLitBits + 1, &sm.lit, sm.lit_sorted);
+          if (e == 0) { bail = true; break; }
+          if (e < kLitLimit) {
+            if (opos >= cap) { bail = true; break; }
+            if (lane == 0) out[opos] = (uint8_t)(e >> 4);
+            opos++;
+            fb.drop((int)(e & 15u));
+            continue;
           }
-          fb.drop((int)(d & 15u));
-          if ((d >> 8) & 3u) { bail = true; break; }
-          const uint32_t dist = (d >> 16) + fb.take((int)((d >> 4) & 15u));
-          if (dist > opos || (uint64_t)opos + length > cap) { bail = true; break; }
-          __syncwarp();
-          uint8_t *dp = out + opos;
-          const uint8_t *sp8 = dp - dist;
-          if (dist >= 32) {
-            for (uint32_t base = 0; base < length; base += 32) {
-              const uint32_t i = base + lane;
-              if (i < length) dp[i] = sp8[i];
-              __syncwarp();
-            }
-          } else {
-            for (uint32_t i = lane; i < length; i += 32) dp[i] = sp8[i % dist];
+        }
+        fb.drop((int)(e & 15u));
+        const uint32_t sym = e >> 4;
+        if (sym == (uint32_t)kEob) break;
+        if (sym >= (uint32_t)kNumLit) { bail = true; break; }
+        // length base + extra bits (inflate.mbt:591-627), uniform index -> constant-cache broadcast
+        const uint32_t lt = c_len_tab[sym - 257u];
+        const uint32_t length = (lt & 0xffffu) + fb.take((int)(lt >> 16));
+        fb.refill();
+        uint32_t d = sm.dist_lut[fb.peek() & ((1u << kFastDistBits) - 1u)];
+        if (d == 0) {
+          d = canon_long(fb.peek(), kFastDistBits + 1, &sm.dist, sm.dist_sorted);
+          if (d == 0) { bail = true; break; }
+        }
+        fb.drop((int)(d & 15u));
+        if ((d >> 4) >= (uint32_t)kNumDist) { bail = true; break; }
+        const uint32_t dt = c_dist_tab[d >> 4]; // distance base + extra bits (inflate.mbt:656-674)
+        const uint32_t dist = (dt & 0xffffu) + fb.take((int)(dt >> 16));
+        if (dist > opos || length > cap - opos) { bail = true; break; }
+        // retire the previous deferred copy, then make lane-0 literal stores visible to the copy loads
+        if (pend_ptr) { *pend_ptr = (uint8_t)pend_val; pend_ptr = nullptr; }
+        __syncwarp();
+        uint8_t *dp = out + opos;
+        const uint8_t *sp8 = dp - dist;
+        if (length <= 32u) { // one step: load now, store at the next match / block end
+          if ((uint32_t)lane < length) {
+            uint32_t i = (uint32_t)lane;
+            if (dist < 32u) i -= ((i * c_recip[dist]) >> 16) * dist; // i % dist: the pattern repeats
+            pend_val = sp8[i];
+            pend_ptr = dp + lane;
+          }
+        } else if (dist >= 32u) {
+          for (uint32_t base = 0; base < length; base += 32) {
+            const uint32_t i = base + lane;
+            if (i < length) dp[i] = sp8[i];
             __syncwarp();
           }
-          opos += length;
-          lim = cap - opos < 32u ? cap - opos : 32u;
+        } else {
+          const uint32_t r = c_recip[dist];
+          for (uint32_t i = lane; i < length; i += 32) dp[i] = sp8[i - ((i * r) >> 16) * dist];
+          __syncwarp();
         }
-        continue;
-      literal_long: {
-          int nn;
-          const int sym = canon_long(fb.peek(), kFastLitBits + 1, &sm.lit, sm.lit_sorted, &nn);
-          if (sym < 0) { bail = true; break; }
-          e = lit_entry(sym, nn);
-          goto have_entry;
-        }
+        opos += length;
       }
+      if (pend_ptr) { *pend_ptr = (uint8_t)pend_val; pend_ptr = nullptr; }
+      __syncwarp();
       if (bail) break;
       if (final_flag) done = true;
       // bits consumed beyond the real input mean the stream is truncated: exact path
@@ -838,7 +837,7 @@ void launch_inflate(const InflateJob &j, int num_sms, cudaStream_t st)
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     const char *e = getenv("FB200_INFLATE_CTAS");
-    ctas_per_sm = e ? atoi(e) : 8;
+    ctas_per_sm = e ? atoi(e) : 12;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
   uint64_t want = (j.nstreams + kFastWarps - 1) / kFastWarps;
