@@ -52,14 +52,42 @@ __global__ void k_init_sched()
 
 constexpr unsigned kFull = 0xffffffffu;
 
-template <bool MULTI>
-__global__ void k_parse(DeflateJob j, uint32_t *counter)
+// match_len tail (deflate-fast.mbt:286-307): number of equal bytes of src[s2..] and src[t..], at most a,
+// given that the first `from` already matched.  32 bytes per step; long matches take four steps per
+// round trip to memory.
+__device__ __forceinline__ int match_tail(const uint8_t *srcb, int s2, int t, int a, int from, int lane)
 {
-  using T = typename std::conditional<MULTI, uint32_t, uint16_t>::type;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5;
+  const uint8_t *ps = srcb + s2 + lane, *pt = srcb + t + lane;
+  int off = from;
+  while (off < a) {
+    if (a - off > 32) {
+      bool mism[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int i = off + 32 * k + lane;
+        mism[k] = (i >= a) || (__ldg(ps + off + 32 * k) != __ldg(pt + off + 32 * k));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned mm = __ballot_sync(kFull, mism[k]);
+        if (mm) return off + 32 * k + __ffs(mm) - 1;
+      }
+      off += 128;
+    } else {
+      const int i = off + lane;
+      const bool mism = (i >= a) || (__ldg(ps + off) != __ldg(pt + off));
+      const unsigned mm = __ballot_sync(kFull, mism);
+      if (mm) return off + __ffs(mm) - 1;
+      off += 32;
+    }
+  }
+  return a;
+}
+
+template <bool MULTI, typename T, bool GTAB>
+__device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table)
+{
   const int lane = threadIdx.x & 31;
-  T *table = reinterpret_cast<T *>(smem_raw) + (size_t)warp * kTableSize;
   const unsigned lt_mask = (1u << lane) - 1;
   const unsigned gt_mask = ~((2u << lane) - 1); // lanes above this one (0 for lane 31)
 
@@ -119,9 +147,14 @@ __global__ void k_parse(DeflateJob j, uint32_t *counter)
           const uint32_t h = hash4(cv);
           T *slot = table + h;
           const T old = *slot;
-          __syncwarp();
           const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
-          *slot = mine;
+          unsigned conf;
+          if (GTAB) { // table in global memory: no dependent read-back, compare buckets across lanes instead
+            conf = __ballot_sync(kFull, (__match_any_sync(kFull, h) & lt_mask) != 0);
+          } else {
+            __syncwarp();
+            *slot = mine;
+          }
           int cand;
           bool ok;
           if (MULTI) {
@@ -157,52 +190,50 @@ __global__ void k_parse(DeflateJob j, uint32_t *counter)
             if (avail >= 4) extl = (e1 < 4 || avail == 4) ? e1 : 4 + e2;
             if (cand + 4 < 0) { extl = 0; avail = 99; } // candidate in the previous block: match_len == 0 (D1)
           }
-          __syncwarp();
-          const T rb = *slot;
-          const unsigned conf = __ballot_sync(kFull, rb != mine);
+          if (!GTAB) {
+            __syncwarp();
+            const T rb = *slot;
+            conf = __ballot_sync(kFull, rb != mine);
+            // final table state is written below: restore every bucket first
+            *slot = old;
+          }
           unsigned hitm = __ballot_sync(kFull, hit);
           const int W = conf ? __ffs(conf) - 1 : 32;
-          // final table state is written below: restore every bucket first
-          *slot = old;
           if (W >= 2) {
-            if (W < 32) hitm &= (1u << W) - 1u;
-            unsigned keep = 0;
+            const unsigned wmask = (W < 32 ? (1u << W) : 0u) - 1u; // lanes below W
+            hitm &= wmask;
+            // Walk the matches of the prefix.  Only masks are updated per match: `keep` = lanes whose
+            // insert happens, `emit` = lanes that produce a token (literal lanes and match lanes);
+            // the tokens themselves are stored once, after the walk, at ntok + rank within `emit`.
+            unsigned keep = 0, emit = 0;
+            int my_ext = extl;
             int cur = 1;
             bool block_done = false;
+            const int packed_mine = (extl << 1) | (extl == avail ? 1 : 0);
             for (;;) {
-              const unsigned hm = hitm & ~((1u << cur) - 1u);
+              const unsigned below = (1u << cur) - 1u;
+              const unsigned hm = hitm & ~below;
               if (hm == 0) { // no further hit below W: lanes cur..W-1 are literals, probing continues at lane W
-                keep |= ((W < 32 ? (1u << W) : 0u) - 1u) & ~((1u << (cur - 1)) - 1u);
-                if (lane >= cur && lane < W) tok[ntok + (uint32_t)(lane - cur)] = cv & 0xffu;
-                ntok += (uint32_t)(W - cur);
+                keep |= wmask & ~(below >> 1);
+                emit |= wmask & ~below;
                 next_emit = base + W;
                 modeM = false; loop_p0 = base + cur + 1; k0 = W - 1 - cur;
                 break;
               }
               const int m = __ffs(hm) - 1;
-              keep |= ((2u << m) - 1u) & ~((1u << (cur - 1)) - 1u);
-              if (lane >= cur && lane < m) tok[ntok + (uint32_t)(lane - cur)] = cv & 0xffu;
-              ntok += (uint32_t)(m - cur);
-              const int packed = __shfl_sync(kFull, (extl << 1) | (extl == avail ? 1 : 0), m);
+              const unsigned upto = (2u << m) - 1u;
+              keep |= upto & ~(below >> 1);
+              emit |= upto & ~below; // literals cur..m-1, match at m
+              const int packed = __shfl_sync(kFull, packed_mine, m);
               int ext = packed >> 1;
               const int s2 = base + m + 4;
-              if (packed & 1) { // the speculative bytes all matched: keep comparing, 32 bytes per step
+              if (packed & 1) { // the speculative bytes all matched: keep comparing
                 const int t = __shfl_sync(kFull, cand, m) + 4;
                 int s1 = s2 + kMaxMatchLength - 4;
                 if (s1 > n) s1 = n;
-                const int a = s1 - s2;
-                int e = a;
-                for (int off = ext; off < a; off += 32) {
-                  const int i = off + lane;
-                  const bool mism = (i >= a) || (__ldg(srcb + s2 + i) != __ldg(srcb + t + i));
-                  const unsigned mm = __ballot_sync(kFull, mism);
-                  if (mm) { e = off + __ffs(mm) - 1; break; }
-                }
-                ext = e;
+                ext = match_tail(srcb, s2, t, s1 - s2, ext, lane);
+                if (lane == m) my_ext = ext;
               }
-              if (lane == m) // match_token(l + 4 - 3, s - t - 1) (:228-233)
-                tok[ntok] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(pos - cand - 1);
-              ntok++;
               s = s2 + ext;
               next_emit = s;
               if (s >= s_limit) { block_done = true; break; } // :236-238
@@ -210,7 +241,14 @@ __global__ void k_parse(DeflateJob j, uint32_t *counter)
               if (ncur >= W) break; // next batch starts at s (still post-match mode)
               cur = ncur;
             }
-            __syncwarp();
+            if ((emit >> lane) & 1u) {
+              uint32_t t = cv & 0xffu; // emit_literal (:273-279)
+              if ((hitm >> lane) & 1u) // match_token(l + 4 - 3, s - t - 1) (:228-233)
+                t = kMatchType + ((uint32_t)(my_ext + 1) << kLengthShift) + (uint32_t)(pos - cand - 1);
+              tok[ntok + (uint32_t)__popc(emit & lt_mask)] = t;
+            }
+            ntok += (uint32_t)__popc(emit);
+            if (!GTAB) __syncwarp();
             if ((keep >> lane) & 1u) *slot = mine; // kept lanes share no bucket
             __syncwarp();
             if (block_done) break;
@@ -295,14 +333,7 @@ __global__ void k_parse(DeflateJob j, uint32_t *counter)
         if (t >= 0) {
           int s1 = s2 + kMaxMatchLength - 4;
           if (s1 > n) s1 = n;
-          const int a = s1 - s2;
-          ext = a;
-          for (int base = 0; base < a; base += 32) {
-            const int i = base + lane;
-            const bool mism = (i >= a) || (__ldg(srcb + s2 + i) != __ldg(srcb + t + i));
-            const unsigned mm = __ballot_sync(kFull, mism);
-            if (mm) { ext = base + __ffs(mm) - 1; break; }
-          }
+          ext = match_tail(srcb, s2, t, s1 - s2, 0, lane);
         }
         if (lane == 0) // match_token(l + 4 - 3, s - t - 1) (:228-233)
           tok[ntok] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1);
@@ -321,28 +352,57 @@ __global__ void k_parse(DeflateJob j, uint32_t *counter)
   }
 }
 
+// Warps [0, smem_warps) of a CTA keep their table in shared memory; the others
+// (the kernel is latency bound and shared memory caps it at 7 tables per SM)
+// keep theirs in a global scratch area that stays L2 resident.
+template <bool MULTI>
+__global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *gtables)
+{
+  using T = typename std::conditional<MULTI, uint32_t, uint16_t>::type;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  if (warp < smem_warps) {
+    parse_worker<MULTI, T, false>(j, counter, reinterpret_cast<T *>(smem_raw) + (size_t)warp * kTableSize);
+  } else {
+    const int gw = (int)(blockDim.x >> 5) - smem_warps;
+    T *table = reinterpret_cast<T *>(gtables) + ((size_t)blockIdx.x * gw + (warp - smem_warps)) * kTableSize;
+    parse_worker<MULTI, T, true>(j, counter, table);
+  }
+}
+
 void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
 
-static int g_parse_occ_single = 0, g_parse_occ_multi = 0;
+static int g_parse_occ_single = 0, g_parse_occ_multi = 0, g_parse_gwarps = 0;
+static void *g_parse_gtables = nullptr;
 
 void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
 {
   static bool inited = false;
   if (!inited) {
     const char *e = getenv("FB200_PARSE_WARPS");
-    int w = e ? atoi(e) : 7;
-    if (w < 1) w = 1;
+    int w = e ? atoi(e) : 4;
+    if (w < 0) w = 0;
     if (w > 7) w = 7;
+    const char *g = getenv("FB200_PARSE_GWARPS");
+    int gw = g ? atoi(g) : 20;
+    if (gw < 0) gw = 0;
+    if (gw > 25) gw = 25;
+    if (w + gw == 0) w = 1;
     g_parse_occ_single = w;
     g_parse_occ_multi = w > 3 ? 3 : w;
+    g_parse_gwarps = gw;
+    if (gw) cudaMalloc(&g_parse_gtables, (size_t)num_sms * gw * kTableSize * 4);
     cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_parse_occ_single * kTableSize * 2);
     cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_parse_occ_multi * kTableSize * 4);
     inited = true;
   }
-  k_parse<false><<<num_sms, g_parse_occ_single * 32, g_parse_occ_single * kTableSize * 2, st>>>(j, j.counters + 0);
-  k_parse<true><<<num_sms, g_parse_occ_multi * 32, g_parse_occ_multi * kTableSize * 4, st>>>(j, j.counters + 1);
+  const int gw = g_parse_gwarps;
+  k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * 2, st>>>(
+      j, j.counters + 0, g_parse_occ_single, g_parse_gtables);
+  k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4, st>>>(
+      j, j.counters + 1, g_parse_occ_multi, g_parse_gtables);
 }
 
 // ------------------------------------------------------------------

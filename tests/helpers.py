@@ -165,6 +165,9 @@ class HostModel:
         L.fbm_codes.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         L.fbm_parse_stream.restype = C.c_int64
         L.fbm_parse_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.fbm_parse_stream_v2.restype = C.c_int64
+        L.fbm_parse_stream_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                          C.c_void_p]
 
     def generate(self, freq, max_bits):
         f = np.ascontiguousarray(np.asarray(freq, dtype=np.uint32))
@@ -173,15 +176,26 @@ class HostModel:
         self.L.fbm_generate(f.ctypes.data, f.size, max_bits, lens.ctypes.data, codes.ctypes.data)
         return lens, codes
 
-    def parse_stream(self, data: bytes):
+    def parse_stream(self, data: bytes, v2: bool = False):
         n = len(data)
         a = np.frombuffer(data, dtype=np.uint8)
         nb_cap = n // 65535 + 2
         toks = np.zeros(n + 16, np.uint32)
         ntok = np.zeros(nb_cap, np.uint32)
-        tot = self.L.fbm_parse_stream(a.ctypes.data if n else None, n, toks.ctypes.data, n + 16, ntok.ctypes.data, nb_cap)
+        if v2:
+            stats = np.zeros(4, np.uint64)
+            tot = self.L.fbm_parse_stream_v2(a.ctypes.data if n else None, n, toks.ctypes.data, n + 16,
+                                             ntok.ctypes.data, nb_cap, stats.ctypes.data)
+        else:
+            tot = self.L.fbm_parse_stream(a.ctypes.data if n else None, n, toks.ctypes.data, n + 16,
+                                          ntok.ctypes.data, nb_cap)
         assert tot >= 0
         return toks[:tot], ntok[: (n + 65534) // 65535]
+
+    def codes(self, xlen: int, xoff: int):
+        out = (C.c_int * 6)()
+        self.L.fbm_codes(xlen, xoff, out)
+        return list(out)
 
     def build_block(self, freq320, kind, n):
         f = np.ascontiguousarray(np.asarray(freq320, dtype=np.uint32)).copy()
