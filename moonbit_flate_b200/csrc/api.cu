@@ -58,9 +58,15 @@ struct fb200_ctx {
   // deflate scratch
   DevBuf stream_blk0, stream_bytes, stream_trailer, dst_off_own, blk_stream, blk_ntok, blk_kind, blk_bits,
       blk_bit_start, blk_hdr_nbits, blk_hdr, blk_freq, blk_code, tokens, counters;
-  // staging for the host-buffer entry points
-  DevBuf h_src, h_src_off, h_dst, h_dst_off;
-  DevBuf i_comp, i_comp_off, i_out, i_out_off, i_out_len, i_status, i_err_off, i_consumed, i_fallback;
+  // staging for the host-buffer entry points: two slots, so that the H2D copy of chunk c+1 and the
+  // D2H copy of chunk c-1 overlap the kernels of chunk c (copy engines run beside the SMs)
+  DevBuf h_src_off; // fixed-size segment offsets of the *_segments_dev entry point
+  DevBuf p_in[2], p_out[2], p_off_in[2], p_off_out[2], p_off_abs[2], p_len[2], p_status[2], p_eoff[2], p_cons[2];
+  DevBuf all_off, all_off2;
+  DevBuf i_fallback;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t e_in[2] = {}, e_comp[2] = {}, e_out[2] = {};
+  uint64_t chunk_bytes = 128ull << 20;
   uint64_t *pinned = nullptr; // small pinned read-back area
   // last deflate job (for introspection)
   DeflateJob last{};
@@ -123,6 +129,17 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
     cudaEventCreate(&ctx->ev0[i]);
     cudaEventCreate(&ctx->ev1[i]);
   }
+  cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&ctx->e_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->e_comp[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->e_out[i], cudaEventDisableTiming);
+  }
+  if (const char *e = getenv("FB200_CHUNK_MB")) {
+    const long mb = atol(e);
+    if (mb > 0) ctx->chunk_bytes = (uint64_t)mb << 20;
+  }
   launch_init_tables(ctx->stream);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
     delete ctx;
@@ -139,9 +156,18 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
   cudaSetDevice(ctx->device);
   DevBuf *all[] = {&ctx->stream_blk0, &ctx->stream_bytes, &ctx->stream_trailer, &ctx->dst_off_own, &ctx->blk_stream,
                    &ctx->blk_ntok, &ctx->blk_kind, &ctx->blk_bits, &ctx->blk_bit_start, &ctx->blk_hdr_nbits,
-                   &ctx->blk_hdr, &ctx->blk_freq, &ctx->blk_code, &ctx->tokens, &ctx->counters, &ctx->h_src,
-                   &ctx->h_src_off, &ctx->h_dst, &ctx->h_dst_off, &ctx->i_comp, &ctx->i_comp_off, &ctx->i_out,
-                   &ctx->i_out_off, &ctx->i_out_len, &ctx->i_status, &ctx->i_err_off, &ctx->i_consumed, &ctx->i_fallback};
+                   &ctx->blk_hdr, &ctx->blk_freq, &ctx->blk_code, &ctx->tokens, &ctx->counters, &ctx->h_src_off,
+                   &ctx->all_off, &ctx->all_off2, &ctx->i_fallback};
+  for (int i = 0; i < 2; i++) {
+    DevBuf *slot[] = {&ctx->p_in[i], &ctx->p_out[i], &ctx->p_off_in[i], &ctx->p_off_out[i], &ctx->p_off_abs[i],
+                      &ctx->p_len[i], &ctx->p_status[i], &ctx->p_eoff[i], &ctx->p_cons[i]};
+    for (DevBuf *b : slot) b->release();
+    if (ctx->e_in[i]) cudaEventDestroy(ctx->e_in[i]);
+    if (ctx->e_comp[i]) cudaEventDestroy(ctx->e_comp[i]);
+    if (ctx->e_out[i]) cudaEventDestroy(ctx->e_out[i]);
+  }
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   for (DevBuf *b : all) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < FB200_NUM_STAGES; i++) {
@@ -243,7 +269,7 @@ static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
   launch_histogram(j, st);
   ctx->stage_end(FB200_STAGE_HISTOGRAM);
   ctx->stage_begin(FB200_STAGE_BUILD);
-  launch_build_codes(j, st);
+  launch_build_codes(j, ctx->num_sms, st);
   ctx->stage_end(FB200_STAGE_BUILD);
   ctx->stage_begin(FB200_STAGE_LAYOUT);
   launch_layout(j, st);
@@ -308,29 +334,120 @@ extern "C" int fb200_deflate_segments_dev(fb200_ctx *ctx, const uint8_t *d_src, 
   return rc;
 }
 
+// Host-buffer deflate: the batch is cut into chunks of whole streams (~chunk_bytes each) that flow
+// through a two-slot pipeline -- H2D of chunk c+1 (stream s_in) and D2H of chunk c-1 (s_out) run
+// beside the kernels of chunk c (ctx->stream).  Streams are independent, so chunking never changes
+// a byte; offsets are re-based per chunk on the device.
+struct HostChunk {
+  uint64_t a, b;        // streams [a, b)
+  uint64_t byte0, bytes; // source byte range
+};
+
 static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, const uint64_t *src_off, uint64_t ns,
                                uint64_t seg_size, uint8_t *dst, uint64_t dst_cap, uint64_t *dst_off, uint64_t *out_len)
 {
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  CK(ctx->h_src.ensure(n + 16));
-  CK(ctx->h_src_off.ensure((ns + 1) * 8));
-  CK(ctx->h_dst_off.ensure((ns + 1) * 8));
-  if (n) CK(cudaMemcpyAsync(ctx->h_src.p, src, n, cudaMemcpyHostToDevice, st));
-  if (src_off) CK(cudaMemcpyAsync(ctx->h_src_off.p, src_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
-  else launch_fill_seg_off(ctx->h_src_off.as<uint64_t>(), ns, seg_size, n, st);
-  uint64_t total = 0;
-  int rc = deflate_phase_a(ctx, ctx->h_src.as<uint8_t>(), ctx->h_src_off.as<uint64_t>(), ns, n,
-                           ctx->h_dst_off.as<uint64_t>(), &total);
+  *out_len = 0;
+  if (ns == 0) {
+    if (dst_off) dst_off[0] = 0;
+    ctx->stats = fb200_stats{};
+    ctx->last = DeflateJob{};
+    return FB200_OK;
+  }
+  std::vector<HostChunk> chunks;
+  {
+    uint64_t a = 0;
+    while (a < ns) {
+      uint64_t b = a;
+      const uint64_t byte0 = src_off ? src_off[a] : a * seg_size;
+      uint64_t bytes = 0;
+      if (src_off) {
+        while (b < ns && (b == a || bytes < ctx->chunk_bytes)) { b++; bytes = src_off[b] - byte0; }
+      } else {
+        uint64_t cnt = ctx->chunk_bytes / seg_size;
+        if (cnt == 0) cnt = 1;
+        b = a + cnt < ns ? a + cnt : ns;
+        const uint64_t end = b * seg_size < n ? b * seg_size : n;
+        bytes = end - byte0;
+      }
+      chunks.push_back({a, b, byte0, bytes});
+      a = b;
+    }
+  }
+  uint64_t max_bytes = 0, max_cnt = 0;
+  for (const HostChunk &c : chunks) {
+    if (c.bytes > max_bytes) max_bytes = c.bytes;
+    if (c.b - c.a > max_cnt) max_cnt = c.b - c.a;
+  }
+  for (int i = 0; i < 2; i++) {
+    CK(ctx->p_in[i].ensure(max_bytes + 16));
+    CK(ctx->p_off_in[i].ensure((max_cnt + 1) * 8));
+    CK(ctx->p_off_out[i].ensure((max_cnt + 1) * 8));
+    CK(ctx->p_off_abs[i].ensure((max_cnt + 1) * 8));
+    if (chunks.size() > 1) CK(ctx->p_out[i].ensure(max_bytes / 2 + max_bytes / 8 + (1u << 20))); // grows if needed
+  }
+  if (src_off) {
+    CK(ctx->all_off.ensure((ns + 1) * 8));
+    CK(cudaMemcpyAsync(ctx->all_off.p, src_off, (ns + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+  }
+  auto issue_h2d = [&](size_t c) -> int {
+    const HostChunk &ch = chunks[c];
+    const int slot = (int)(c & 1);
+    if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ctx->e_comp[slot], 0));
+    if (ch.bytes) CK(cudaMemcpyAsync(ctx->p_in[slot].p, src + ch.byte0, ch.bytes, cudaMemcpyHostToDevice, ctx->s_in));
+    if (src_off)
+      launch_affine_u64(ctx->p_off_in[slot].as<uint64_t>(), ctx->all_off.as<uint64_t>() + ch.a, ch.b - ch.a + 1,
+                        0ull - ch.byte0, ctx->s_in);
+    else
+      launch_fill_seg_off(ctx->p_off_in[slot].as<uint64_t>(), ch.b - ch.a, seg_size, ch.bytes, ctx->s_in);
+    CK(cudaEventRecord(ctx->e_in[slot], ctx->s_in));
+    return FB200_OK;
+  };
+  int rc = issue_h2d(0);
   if (rc != FB200_OK) return rc;
-  *out_len = total;
-  if (total > dst_cap) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
-  CK(ctx->h_dst.ensure(total + 16));
-  rc = deflate_phase_b(ctx, ctx->h_dst.as<uint8_t>(), total);
-  if (rc != FB200_OK) return rc;
-  CK(cudaMemcpyAsync(dst, ctx->h_dst.p, total, cudaMemcpyDeviceToHost, st));
-  if (dst_off) CK(cudaMemcpyAsync(dst_off, ctx->h_dst_off.p, (ns + 1) * 8, cudaMemcpyDeviceToHost, st));
+  uint64_t base = 0, nblocks = 0, launches = 0;
+  bool overflow = false;
+  for (size_t c = 0; c < chunks.size(); c++) {
+    const HostChunk &ch = chunks[c];
+    const int slot = (int)(c & 1);
+    if (c + 1 < chunks.size() && (rc = issue_h2d(c + 1)) != FB200_OK) return rc;
+    CK(cudaStreamWaitEvent(st, ctx->e_in[slot], 0));
+    uint64_t total = 0;
+    rc = deflate_phase_a(ctx, ctx->p_in[slot].as<uint8_t>(), ctx->p_off_in[slot].as<uint64_t>(), ch.b - ch.a, ch.bytes,
+                         ctx->p_off_out[slot].as<uint64_t>(), &total);
+    if (rc != FB200_OK) return rc;
+    nblocks += ctx->stats.nblocks;
+    launches += ctx->stats.kernel_launches + 2;
+    if (base + total > dst_cap) overflow = true;
+    if (!overflow) {
+      if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->e_out[slot], 0));
+      CK(ctx->p_out[slot].ensure(total + 16));
+      rc = deflate_phase_b(ctx, ctx->p_out[slot].as<uint8_t>(), total);
+      if (rc != FB200_OK) return rc;
+      launches += 2;
+      if (dst_off)
+        launch_affine_u64(ctx->p_off_abs[slot].as<uint64_t>(), ctx->p_off_out[slot].as<uint64_t>(), ch.b - ch.a + 1,
+                          base, st);
+      CK(cudaEventRecord(ctx->e_comp[slot], st));
+      CK(cudaStreamWaitEvent(ctx->s_out, ctx->e_comp[slot], 0));
+      if (total) CK(cudaMemcpyAsync(dst + base, ctx->p_out[slot].p, total, cudaMemcpyDeviceToHost, ctx->s_out));
+      if (dst_off)
+        CK(cudaMemcpyAsync(dst_off + ch.a, ctx->p_off_abs[slot].p, (ch.b - ch.a + 1) * 8, cudaMemcpyDeviceToHost,
+                           ctx->s_out));
+      CK(cudaEventRecord(ctx->e_out[slot], ctx->s_out));
+    } else {
+      CK(cudaEventRecord(ctx->e_comp[slot], st));
+    }
+    base += total;
+  }
+  CK(cudaStreamSynchronize(ctx->s_in));
+  CK(cudaStreamSynchronize(ctx->s_out));
   CK(cudaStreamSynchronize(st));
+  *out_len = base; // on overflow: the capacity the call needs
+  ctx->stats.nblocks = nblocks;
+  ctx->stats.kernel_launches = launches;
+  if (overflow) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
   return FB200_OK;
 }
 
@@ -457,35 +574,86 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
   if (!ctx || !comp_off || !out_off || !out_len || !status || !err_off) return FB200_ERR_ARG;
   for (uint64_t i = 0; i < nstreams; i++)
     if (comp_off[i + 1] < comp_off[i] || out_off[i + 1] < out_off[i]) { ctx->err = "offsets not monotone"; return FB200_ERR_ARG; }
-  const uint64_t nc = nstreams ? comp_off[nstreams] : 0;
-  const uint64_t no = nstreams ? out_off[nstreams] : 0;
+  const uint64_t nc = nstreams ? comp_off[nstreams] - comp_off[0] : 0;
+  const uint64_t no = nstreams ? out_off[nstreams] - out_off[0] : 0;
   if ((!comp && nc) || (!out && no)) return FB200_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  ctx->stats = fb200_stats{};
+  if (nstreams == 0) return FB200_OK;
   cudaStream_t st = ctx->stream;
-  CK(ctx->i_comp.ensure(nc + 16));
-  CK(ctx->i_comp_off.ensure((nstreams + 1) * 8));
-  CK(ctx->i_out.ensure(no + 16));
-  CK(ctx->i_out_off.ensure((nstreams + 1) * 8));
-  CK(ctx->i_out_len.ensure((nstreams + 1) * 8));
-  CK(ctx->i_status.ensure((nstreams + 1) * 4));
-  CK(ctx->i_err_off.ensure((nstreams + 1) * 8));
-  CK(ctx->i_consumed.ensure((nstreams + 1) * 8));
-  if (nc) CK(cudaMemcpyAsync(ctx->i_comp.p, comp, nc, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->i_comp_off.p, comp_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->i_out_off.p, out_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, st));
-  int rc = fb200_inflate_batch_dev(ctx, ctx->i_comp.as<uint8_t>(), ctx->i_comp_off.as<uint64_t>(), nstreams,
-                                   ctx->i_out.as<uint8_t>(), ctx->i_out_off.as<uint64_t>(),
-                                   ctx->i_out_len.as<uint64_t>(), ctx->i_status.as<int32_t>(),
-                                   ctx->i_err_off.as<int64_t>(), ctx->i_consumed.as<uint64_t>());
-  if (rc != FB200_OK) return rc;
-  if (no) CK(cudaMemcpyAsync(out, ctx->i_out.p, no, cudaMemcpyDeviceToHost, st));
-  if (nstreams) {
-    CK(cudaMemcpyAsync(out_len, ctx->i_out_len.p, nstreams * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(status, ctx->i_status.p, nstreams * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(err_off, ctx->i_err_off.p, nstreams * 8, cudaMemcpyDeviceToHost, st));
-    if (consumed) CK(cudaMemcpyAsync(consumed, ctx->i_consumed.p, nstreams * 8, cudaMemcpyDeviceToHost, st));
+  // chunks of whole streams, two-slot pipeline as in deflate_host_common
+  struct Chunk { uint64_t a, b; };
+  std::vector<Chunk> chunks;
+  uint64_t max_c = 0, max_o = 0, max_cnt = 0;
+  for (uint64_t a = 0; a < nstreams;) {
+    uint64_t b = a;
+    while (b < nstreams && (b == a || (out_off[b] - out_off[a] < ctx->chunk_bytes && comp_off[b] - comp_off[a] < ctx->chunk_bytes)))
+      b++;
+    chunks.push_back({a, b});
+    if (comp_off[b] - comp_off[a] > max_c) max_c = comp_off[b] - comp_off[a];
+    if (out_off[b] - out_off[a] > max_o) max_o = out_off[b] - out_off[a];
+    if (b - a > max_cnt) max_cnt = b - a;
+    a = b;
   }
+  for (int i = 0; i < 2; i++) {
+    CK(ctx->p_in[i].ensure(max_c + 16));
+    CK(ctx->p_out[i].ensure(max_o + 16));
+    CK(ctx->p_off_in[i].ensure((max_cnt + 1) * 8));
+    CK(ctx->p_off_out[i].ensure((max_cnt + 1) * 8));
+    CK(ctx->p_len[i].ensure((max_cnt + 1) * 8));
+    CK(ctx->p_status[i].ensure((max_cnt + 1) * 4));
+    CK(ctx->p_eoff[i].ensure((max_cnt + 1) * 8));
+    CK(ctx->p_cons[i].ensure((max_cnt + 1) * 8));
+  }
+  CK(ctx->all_off.ensure((nstreams + 1) * 8));
+  CK(ctx->all_off2.ensure((nstreams + 1) * 8));
+  CK(cudaMemcpyAsync(ctx->all_off.p, comp_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+  CK(cudaMemcpyAsync(ctx->all_off2.p, out_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+  auto issue_h2d = [&](size_t c) -> int {
+    const Chunk &ch = chunks[c];
+    const int slot = (int)(c & 1);
+    const uint64_t cb = comp_off[ch.b] - comp_off[ch.a];
+    if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ctx->e_comp[slot], 0));
+    if (cb) CK(cudaMemcpyAsync(ctx->p_in[slot].p, comp + comp_off[ch.a], cb, cudaMemcpyHostToDevice, ctx->s_in));
+    launch_affine_u64(ctx->p_off_in[slot].as<uint64_t>(), ctx->all_off.as<uint64_t>() + ch.a, ch.b - ch.a + 1,
+                      0ull - comp_off[ch.a], ctx->s_in);
+    launch_affine_u64(ctx->p_off_out[slot].as<uint64_t>(), ctx->all_off2.as<uint64_t>() + ch.a, ch.b - ch.a + 1,
+                      0ull - out_off[ch.a], ctx->s_in);
+    CK(cudaEventRecord(ctx->e_in[slot], ctx->s_in));
+    return FB200_OK;
+  };
+  int rc = issue_h2d(0);
+  if (rc != FB200_OK) return rc;
+  uint64_t launches = 0, fallbacks = 0;
+  for (size_t c = 0; c < chunks.size(); c++) {
+    const Chunk &ch = chunks[c];
+    const int slot = (int)(c & 1);
+    const uint64_t cnt = ch.b - ch.a;
+    if (c + 1 < chunks.size() && (rc = issue_h2d(c + 1)) != FB200_OK) return rc;
+    CK(cudaStreamWaitEvent(st, ctx->e_in[slot], 0));
+    if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->e_out[slot], 0));
+    rc = fb200_inflate_batch_dev(ctx, ctx->p_in[slot].as<uint8_t>(), ctx->p_off_in[slot].as<uint64_t>(), cnt,
+                                 ctx->p_out[slot].as<uint8_t>(), ctx->p_off_out[slot].as<uint64_t>(),
+                                 ctx->p_len[slot].as<uint64_t>(), ctx->p_status[slot].as<int32_t>(),
+                                 ctx->p_eoff[slot].as<int64_t>(), ctx->p_cons[slot].as<uint64_t>());
+    if (rc != FB200_OK) return rc;
+    launches += ctx->stats.kernel_launches + 2;
+    fallbacks += ctx->stats.inflate_fallbacks;
+    CK(cudaEventRecord(ctx->e_comp[slot], st));
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->e_comp[slot], 0));
+    const uint64_t ob = out_off[ch.b] - out_off[ch.a];
+    if (ob) CK(cudaMemcpyAsync(out + out_off[ch.a], ctx->p_out[slot].p, ob, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaMemcpyAsync(out_len + ch.a, ctx->p_len[slot].p, cnt * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaMemcpyAsync(status + ch.a, ctx->p_status[slot].p, cnt * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaMemcpyAsync(err_off + ch.a, ctx->p_eoff[slot].p, cnt * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    if (consumed) CK(cudaMemcpyAsync(consumed + ch.a, ctx->p_cons[slot].p, cnt * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    CK(cudaEventRecord(ctx->e_out[slot], ctx->s_out));
+  }
+  CK(cudaStreamSynchronize(ctx->s_in));
+  CK(cudaStreamSynchronize(ctx->s_out));
   CK(cudaStreamSynchronize(st));
+  ctx->stats.kernel_launches = launches;
+  ctx->stats.inflate_fallbacks = fallbacks;
   return FB200_OK;
 }
 

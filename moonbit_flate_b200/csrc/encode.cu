@@ -90,26 +90,41 @@ void launch_histogram(const DeflateJob &j, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------
-// K3: code construction.  One thread per block; arrays live in local memory.
-__global__ void __launch_bounds__(64) k_build_codes(DeflateJob j)
+// K3: code construction.  One warp per block, working set in shared memory (huff_build.cuh).
+constexpr int kBuildWarps = 10;
+
+__global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(DeflateJob j)
 {
-  const uint64_t blk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (blk >= j.nblocks) return;
-  const int kind = j.blk_kind[blk];
-  if (kind == kKindStored) return;
-  const BlockRef r = block_ref(j, blk);
-  const BlockBuild res = build_block_dev(j.blk_freq + blk * kFreqStride, kind, r.n, j.blk_code + blk * kFreqStride,
-                                         j.blk_hdr + blk * kHdrWords);
-  j.blk_kind[blk] = (uint8_t)res.kind;
-  j.blk_hdr_nbits[blk] = res.hdr_nbits;
-  j.blk_bits[blk] = res.blk_bits;
+  extern __shared__ __align__(16) uint8_t build_smem[];
+  HuffScratch &S = reinterpret_cast<HuffScratch *>(build_smem)[threadIdx.x >> 5];
+  const uint64_t nwarps = (uint64_t)gridDim.x * kBuildWarps;
+  for (uint64_t blk = (uint64_t)blockIdx.x * kBuildWarps + (threadIdx.x >> 5); blk < j.nblocks; blk += nwarps) {
+    const int kind = j.blk_kind[blk];
+    if (kind == kKindStored) continue;
+    const BlockRef r = block_ref(j, blk);
+    const BlockBuild res = build_block_warp(j.blk_freq + blk * kFreqStride, kind, r.n, j.blk_code + blk * kFreqStride,
+                                            j.blk_hdr + blk * kHdrWords, S);
+    if ((threadIdx.x & 31) == 0) {
+      j.blk_kind[blk] = (uint8_t)res.kind;
+      j.blk_hdr_nbits[blk] = res.hdr_nbits;
+      j.blk_bits[blk] = res.blk_bits;
+    }
+    __syncwarp();
+  }
 }
 
-void launch_build_codes(const DeflateJob &j, cudaStream_t st)
+void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st)
 {
   if (j.nblocks == 0) return;
-  unsigned g = (unsigned)((j.nblocks + 63) / 64);
-  k_build_codes<<<g, 64, 0, st>>>(j);
+  static bool inited = false;
+  const int smem = kBuildWarps * (int)sizeof(HuffScratch);
+  if (!inited) {
+    cudaFuncSetAttribute(k_build_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    inited = true;
+  }
+  uint64_t want = (j.nblocks + kBuildWarps - 1) / kBuildWarps;
+  unsigned g = (unsigned)(want < (uint64_t)num_sms ? want : (uint64_t)num_sms);
+  k_build_codes<<<g, kBuildWarps * 32, smem, st>>>(j);
 }
 
 // ------------------------------------------------------------------

@@ -1,14 +1,40 @@
 // huff_build.cuh -- K3 building blocks: length-limited canonical code
-// construction, codegen RLE, dynamic-block header.  Pure integer code that
-// compiles for the device (one thread per block in k_build_codes) and for the
-// host (the CPU test-suite checks it against the oracle without a GPU).
+// construction, codegen RLE, dynamic-block header.  One WARP per block.
 //
-//   HuffmanEncoder::bit_counts / assign_encoding_and_size / generate
+//   HuffmanEncoder::generate / bit_counts / assign_encoding_and_size
 //       huffman-code.mbt:112-343
 //   HuffmanBitWriter::generate_codegen / dynamic_size / write_dynamic_header
 //       huffman-bit-writer.mbt:241-360, :421-471
+//
+// The reference's bit_counts is Go's lazy "boundary package-merge": a serial walk
+// of ~2n*L steps.  Here the same package-merge lists are built eagerly, level by
+// level, so that a warp can work on them in parallel:
+//     list_1 = the leaves (ascending (freq, literal)),
+//     list_k = merge(leaves, pairs(list_{k-1})), ties: PAIR FIRST
+// (the reference takes a leaf only if next_char < next_pair, :186-190), each
+// truncated to its first 2n-2 items (the most any level is ever asked for; the
+// truncation loses no pair because a list never has more than 2n-1 items).
+// Walking down from the top level with m_top = 2n-2, m_{k-1} = 2 * (pairs among
+// the first m_k items of list_k) gives the number of leaves each level uses,
+// which is exactly the reference's leaf_counts[max_bits][k]; symbol i (ascending
+// order) gets length #{k : i < leaves_k} (:236-242, :260-278).
+//
+// The code is written once for device and host: FB_PFOR distributes a loop over
+// the 32 lanes on the device and is a plain loop on the host, where the CPU
+// test-suite diffs every output against the oracle (tests/test_hostmodel.py).
 #pragma once
 #include "common.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define FB_LANE ((int)(threadIdx.x & 31))
+#define FB_NLANES 32
+#define FB_WSYNC() __syncwarp()
+#else
+#define FB_LANE 0
+#define FB_NLANES 1
+#define FB_WSYNC() ((void)0)
+#endif
+#define FB_PFOR(i, n) for (int i = FB_LANE; i < (int)(n); i += FB_NLANES)
 
 #if defined(__CUDACC__)
 #define FB_HD __host__ __device__
@@ -31,125 +57,270 @@ FB_HD inline unsigned brev32(unsigned v)
 #endif
 }
 
-
-constexpr int kMaxSyms = 288;
-constexpr int kIntMax = 2147483647;
-
-// HuffmanEncoder::bit_counts (huffman-code.mbt:112-244).  fr[0..n) are the
-// non-zero frequencies in (freq, literal) order, fr[n] = MAX.  Fills
-// bit_count[1..max_bits] and returns max_bits = min(limit, n-1).
-FB_HD inline int bit_counts_dev(const int *fr, int n, int max_bits, int *bit_count)
+FB_HD inline int wsum(int v)
 {
-  if (max_bits > n - 1) max_bits = n - 1;
-  int last_freq[16], next_char[16], next_pair[16], needed[16];
-  unsigned short leaf[16][16];
-  for (int l = 0; l < 16; l++) {
-    last_freq[l] = next_char[l] = next_pair[l] = needed[l] = 0;
-    for (int k = 0; k < 16; k++) leaf[l][k] = 0;
-  }
-  for (int level = 1; level <= max_bits; level++) { // :149-163
-    last_freq[level] = fr[1];
-    next_char[level] = fr[2];
-    next_pair[level] = fr[0] + fr[1];
-    leaf[level][level] = 2;
-    if (level == 1) next_pair[level] = kIntMax;
-  }
-  needed[max_bits] = 2 * n - 4; // :166
-  int level = max_bits;
-  for (;;) { // :170-224
-    if (next_pair[level] == kIntMax && next_char[level] == kIntMax) {
-      needed[level] = 0;
-      next_pair[level + 1] = kIntMax;
-      level++;
-      continue;
-    }
-    const int prev_freq = last_freq[level];
-    if (next_char[level] < next_pair[level]) { // leaf
-      const int nn = leaf[level][level] + 1;
-      last_freq[level] = next_char[level];
-      leaf[level][level] = (unsigned short)nn;
-      next_char[level] = fr[nn];
-    } else { // pair from the level below
-      last_freq[level] = next_pair[level];
-      for (int i = 0; i < level; i++) leaf[level][i] = leaf[level - 1][i];
-      needed[level - 1] = 2;
-    }
-    needed[level]--;
-    if (needed[level] == 0) {
-      if (level == max_bits) break;
-      next_pair[level + 1] = (int)((unsigned)prev_freq + (unsigned)last_freq[level]);
-      level++;
-    } else {
-      while (needed[level - 1] > 0) level--;
-    }
-  }
-  int bits = 1;
-  for (int lv = max_bits; lv > 0; lv--) { // :236-242
-    bit_count[bits] = (int)leaf[max_bits][lv] - (int)leaf[max_bits][lv - 1];
-    bits++;
-  }
-  return max_bits;
+#if defined(__CUDA_ARCH__)
+  return __reduce_add_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
+FB_HD inline int wmin(int v)
+{
+#if defined(__CUDA_ARCH__)
+  return __reduce_min_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
+FB_HD inline int wmax(int v)
+{
+#if defined(__CUDA_ARCH__)
+  return __reduce_max_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
 }
 
-// HuffmanEncoder::generate (:295-343) + assign_encoding_and_size (:250-280).
-// freq[0..nsym) -> len[0..nsym) (0 for unused symbols), code[] bit-reversed.
-FB_HD inline void generate_dev(const uint32_t *freq, int nsym, int max_bits, unsigned char *len, unsigned short *code)
+constexpr int kMaxSyms = 288;
+constexpr int kSortPad = 512;
+
+// Per-warp working set (shared memory on the device).
+struct HuffScratch {
+  uint32_t keys[kSortPad];          // (freq << 9) | literal, ascending == by_frequency (huffman-code.mbt:346-351)
+  uint32_t lista[2 * kMaxSyms];     // package-merge lists (weights), double buffered
+  uint32_t listb[2 * kMaxSyms];
+  uint32_t pairs[kMaxSyms];
+  uint16_t leafpos[16][kMaxSyms];   // position of leaf i in list_k
+  uint32_t run[16];                 // canonical code counters
+  // block assembly
+  uint32_t freq[320];               // lit/len (286) ++ offset (30) histogram
+  uint32_t cgfreq[32];
+  uint8_t len[320];
+  uint16_t code[320];
+  uint8_t cglen[32];
+  uint16_t cgcode[32];
+  uint8_t cg[kNumLit + kNumDist + 4];
+  int misc[8];
+};
+
+#if defined(__CUDA_ARCH__)
+// One package-merge level on the device: each lane owns up to Q leaves and Q pairs; their (branch-free)
+// binary searches advance in lockstep so the shared-memory loads are independent.
+template <int Q, int TOP>
+__device__ __forceinline__ void pm_merge_level(HuffScratch &S, int k, int n, int np, int cap, uint32_t *cur)
 {
-  unsigned int keys[kMaxSyms + 1]; // (freq << 9) | literal: ascending == by_frequency (:346-351)
-  int fr[kMaxSyms + 1];
-  int count = 0;
-  for (int i = 0; i < nsym; i++) {
-    len[i] = 0;
-    code[i] = 0;
-    if (freq[i] != 0) keys[count++] = (freq[i] << 9) | (unsigned)i;
+  int lo[Q];
+  uint32_t w[Q];
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int i = FB_LANE + 32 * q;
+    w[q] = i < n ? (S.keys[i] >> 9) : 0u;
+    lo[q] = 0;
   }
-  if (count <= 2) { // :326-336: codes 0,1 in literal order, length 1
-    for (int i = 0; i < count; i++) {
-      const int sym = keys[i] & 511;
-      len[sym] = 1;
-      code[sym] = (unsigned short)i;
+#pragma unroll
+  for (int step = TOP; step > 0; step >>= 1) { // lo = #pairs with weight <= w
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const int c = lo[q] + step;
+      if (c <= np && S.pairs[c - 1] <= w[q]) lo[q] = c;
     }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int i = FB_LANE + 32 * q;
+    if (i < n) {
+      const int pos = i + lo[q];
+      S.leafpos[k][i] = (uint16_t)pos;
+      if (pos < cap) cur[pos] = w[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int jx = FB_LANE + 32 * q;
+    w[q] = jx < np ? S.pairs[jx] : 0u;
+    lo[q] = 0;
+  }
+#pragma unroll
+  for (int step = TOP; step > 0; step >>= 1) { // lo = #leaves with weight < w
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const int c = lo[q] + step;
+      if (c <= n && (S.keys[c - 1] >> 9) < w[q]) lo[q] = c;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const int jx = FB_LANE + 32 * q;
+    if (jx < np) {
+      const int pos = jx + lo[q];
+      if (pos < cap) cur[pos] = w[q];
+    }
+  }
+}
+#endif
+
+// HuffmanEncoder::generate (:295-343): freq[0..nsym) -> len[] (0 for unused symbols), code[] bit-reversed.
+FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, uint8_t *len, uint16_t *code,
+                                HuffScratch &S)
+{
+  const int P = nsym > 32 ? kSortPad : 32;
+  int nz = 0, first = nsym;
+  FB_PFOR(i, P) {
+    const uint32_t f = i < nsym ? freq[i] : 0u;
+    S.keys[i] = f ? ((f << 9) | (uint32_t)i) : 0xffffffffu;
+    if (f) { nz++; if (i < first) first = i; }
+    if (i < nsym) { len[i] = 0; code[i] = 0; }
+  }
+  const int n = wsum(nz);
+  first = wmin(first);
+  FB_WSYNC();
+  if (n <= 2) { // :326-336: codes 0, 1 in literal order, length 1
+    FB_PFOR(i, nsym) if (freq[i]) { len[i] = 1; code[i] = (uint16_t)(i != first); }
+    FB_WSYNC();
     return;
   }
-  // sort ascending (any correct sort: keys are distinct) -- shell sort
-  for (int gap = count >> 1; gap > 0; gap = (gap == 2) ? 1 : (int)(gap * 5 / 11)) {
-    for (int i = gap; i < count; i++) {
-      const unsigned int v = keys[i];
-      int k = i;
-      while (k >= gap && keys[k - gap] > v) {
-        keys[k] = keys[k - gap];
-        k -= gap;
+  // sort ascending (any correct sort: keys are distinct) -- bitonic network
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#if defined(__CUDA_ARCH__)
+      if (P == kSortPad) { // 8 independent compare-exchanges per lane and stage
+        uint32_t a[8], b[8];
+        int ia[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int t = FB_LANE + 32 * q;
+          ia[q] = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          a[q] = S.keys[ia[q]];
+          b[q] = S.keys[ia[q] | j];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const bool up = (ia[q] & k) == 0;
+          if ((a[q] > b[q]) == up) { S.keys[ia[q]] = b[q]; S.keys[ia[q] | j] = a[q]; }
+        }
+      } else
+#endif
+      FB_PFOR(t, P / 2) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const uint32_t a = S.keys[i], b = S.keys[p];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { S.keys[i] = b; S.keys[p] = a; }
       }
-      keys[k] = v;
+      FB_WSYNC();
     }
   }
-  for (int i = 0; i < count; i++) fr[i] = (int)(keys[i] >> 9);
-  fr[count] = kIntMax; // max_node (:77-79)
-  int bit_count[17];
-  const int mb = bit_counts_dev(fr, count, max_bits, bit_count);
-  // lengths: the `bits` most frequent remaining symbols get length n (:260-278)
-  int end = count;
-  for (int nb = 1; nb <= mb; nb++) {
-    const int bits = bit_count[nb];
-    for (int i = end - bits; i < end; i++) len[keys[i] & 511] = (unsigned char)nb;
-    end -= bits;
+  // package-merge lists (bit_counts :112-244)
+  const int mb = max_bits < n - 1 ? max_bits : n - 1; // :126-129
+  const int cap = 2 * n - 2;
+  uint32_t *prev = S.lista, *cur = S.listb;
+  FB_PFOR(i, n) prev[i] = S.keys[i] >> 9;
+  int plen = n;
+  FB_WSYNC();
+  for (int k = 2; k <= mb; k++) {
+    const int np = plen >> 1;
+    FB_PFOR(j, np) S.pairs[j] = prev[2 * j] + prev[2 * j + 1];
+    FB_WSYNC();
+#if defined(__CUDA_ARCH__)
+    if (n <= 32) pm_merge_level<1, 32>(S, k, n, np, cap, cur);
+    else pm_merge_level<9, 256>(S, k, n, np, cap, cur);
+#else
+    FB_PFOR(i, n) { // leaf i sits after every pair of weight <= its own
+      const uint32_t w = S.keys[i] >> 9;
+      int lo = 0, hi = np;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (S.pairs[mid] <= w) lo = mid + 1; else hi = mid;
+      }
+      const int pos = i + lo;
+      S.leafpos[k][i] = (uint16_t)pos;
+      if (pos < cap) cur[pos] = w;
+    }
+    FB_PFOR(j, np) { // pair j sits after every leaf of weight < its own
+      const uint32_t w = S.pairs[j];
+      int lo = 0, hi = n;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((S.keys[mid] >> 9) < w) lo = mid + 1; else hi = mid;
+      }
+      const int pos = j + lo;
+      if (pos < cap) cur[pos] = w;
+    }
+#endif
+    plen = n + np < cap ? n + np : cap;
+    FB_WSYNC();
+    uint32_t *t = prev; prev = cur; cur = t;
   }
-  // canonical codes in literal order per length, stored bit-reversed (:268-277)
+  // leaves used per level, top down (every lane computes the same values)
+  int nl[17];
+#pragma unroll
+  for (int k = 0; k < 17; k++) nl[k] = 0;
+  {
+    int m = cap;
+    for (int k = mb; k >= 1; k--) {
+      int lv;
+      if (k == 1) lv = m < n ? m : n;
+      else {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if ((int)S.leafpos[k][mid] < m) lo = mid + 1; else hi = mid;
+        }
+        lv = lo;
+      }
+      nl[k] = lv;
+      m = 2 * (m - lv);
+    }
+  }
+  // code length of sorted position i = #{k : i < leaves_k}; counts per length = bit_count[] (:236-242)
+  FB_PFOR(i, n) {
+    int l = 0;
+    for (int k = 1; k <= mb; k++) l += (i < nl[k]);
+    len[S.keys[i] & 511u] = (uint8_t)l;
+  }
+  // canonical codes: per length in literal order, consecutive, stored bit-reversed (:250-280)
   unsigned next_code[17];
-  unsigned c = 0;
-  next_code[0] = 0;
-  for (int nb = 1; nb <= mb; nb++) {
-    c <<= 1;
-    next_code[nb] = c;
-    c += (unsigned)bit_count[nb];
+  {
+    unsigned c = 0;
+    next_code[0] = 0;
+    for (int b = 1; b <= 16; b++) {
+      c <<= 1;
+      next_code[b] = c;
+      // bit_count[b] = leaves_{mb-b+1} - leaves_{mb-b}
+      const int hiK = mb - b + 1, loK = mb - b;
+      if (b <= mb) c += (unsigned)(nl[hiK] - (loK >= 1 ? nl[loK] : 0));
+    }
   }
+  FB_PFOR(i, 16) S.run[i] = 0;
+  FB_WSYNC();
+#if defined(__CUDA_ARCH__)
+  {
+    const int lane = FB_LANE;
+    const unsigned ltm = (1u << lane) - 1u;
+    for (int base = 0; base < nsym; base += 32) {
+      const int i = base + lane;
+      const int l = i < nsym ? (int)len[i] : 0;
+      const unsigned peers = __match_any_sync(0xffffffffu, l);
+      if (l) {
+        const unsigned v = next_code[l] + S.run[l] + (unsigned)__popc(peers & ltm);
+        code[i] = (uint16_t)(__brev(v) >> (32 - l));
+      }
+      __syncwarp();
+      if (l && (peers >> lane) <= 1u) S.run[l] += (unsigned)__popc(peers); // highest lane of each group
+      __syncwarp();
+    }
+  }
+#else
   for (int i = 0; i < nsym; i++) {
     const int l = len[i];
     if (l) {
-      const unsigned v = next_code[l]++;
-      code[i] = (unsigned short)(brev32(v) >> (32 - l));
+      const unsigned v = next_code[l] + S.run[l]++;
+      code[i] = (uint16_t)(brev32(v) >> (32 - l));
     }
   }
+#endif
+  FB_WSYNC();
 }
 
 struct BitAcc {
@@ -175,10 +346,9 @@ struct BitAcc {
   }
 };
 
-
 // Everything write_block_dynamic / write_block_huff decide before the first
 // payload bit (hbw:496-534, :738-787): codes, codegen, "store instead" test,
-// header bit string, exact block size.  freq = lit/len[286] ++ offset[30]
+// header bit string, exact block size.  gfreq = lit/len[286] ++ offset[30]
 // histogram of the block (EOB already counted); kind = kKindDynamic / kKindHuff.
 struct BlockBuild {
   int kind;           // may turn into kKindStored (quirk D2 test)
@@ -186,60 +356,71 @@ struct BlockBuild {
   uint32_t blk_bits;  // header + payload + EOB
 };
 
-FB_HD inline BlockBuild build_block_dev(uint32_t *freq, int kind, uint32_t n, uint32_t *codeout, uint32_t *hdr_words)
+FB_HD inline BlockBuild build_block_warp(const uint32_t *gfreq, int kind, uint32_t n, uint32_t *codeout,
+                                         uint32_t *hdr_words, HuffScratch &S)
 {
   BlockBuild res;
   res.kind = kind;
   res.hdr_nbits = 0;
   res.blk_bits = 0;
-  unsigned char len[kNumLit + kNumDist];
-  unsigned short code[kNumLit + kNumDist];
+  int last_lit = 0, last_off = -1;
+  FB_PFOR(i, 320) {
+    const uint32_t f = i < kNumLit + kNumDist ? gfreq[i] : 0u;
+    S.freq[i] = f;
+    if (f) {
+      if (i < kNumLit) { if (i > last_lit) last_lit = i; }
+      else if (i - kNumLit > last_off) last_off = i - kNumLit;
+    }
+  }
+  last_lit = wmax(last_lit);
+  last_off = wmax(last_off);
+  FB_WSYNC();
   int num_literals, num_offsets;
   if (kind == kKindDynamic) { // index_tokens tail (hbw:574-592)
-    num_literals = kNumLit;
-    while (freq[num_literals - 1] == 0) num_literals--;
-    num_offsets = kNumDist;
-    while (num_offsets > 0 && freq[kNumLit + num_offsets - 1] == 0) num_offsets--;
+    num_literals = last_lit + 1; // >= 257: EOB is counted
+    num_offsets = last_off + 1;
     if (num_offsets == 0) {
-      freq[kNumLit] = 1;
+      if (FB_LANE == 0) S.freq[kNumLit] = 1;
       num_offsets = 1;
+      FB_WSYNC();
     }
-    generate_dev(freq, kNumLit, 15, len, code);
-    generate_dev(freq + kNumLit, kNumDist, 15, len + kNumLit, code + kNumLit);
+    warp_generate(S.freq, kNumLit, 15, S.len, S.code, S);
+    warp_generate(S.freq + kNumLit, kNumDist, 15, S.len + kNumLit, S.code + kNumLit, S);
   } else { // write_block_huff (hbw:747-758): literal-only, static huff_offset (huffman-code.mbt:691)
     num_literals = kEob + 1;
     num_offsets = 1;
-    generate_dev(freq, kNumLit, 15, len, code);
-    for (int i = 0; i < kNumDist; i++) { len[kNumLit + i] = 0; code[kNumLit + i] = 0; }
-    len[kNumLit] = 1;
+    warp_generate(S.freq, kNumLit, 15, S.len, S.code, S);
+    FB_PFOR(i, kNumDist) { S.len[kNumLit + i] = (uint8_t)(i == 0); S.code[kNumLit + i] = 0; }
+    FB_WSYNC();
   }
 
-  // generate_codegen (hbw:241-330)
-  unsigned char cg[kNumLit + kNumDist + 2];
-  uint32_t cgfreq[kNumCodegen];
-  for (int i = 0; i < kNumCodegen; i++) cgfreq[i] = 0;
-  for (int i = 0; i < num_literals; i++) cg[i] = len[i];
-  for (int i = 0; i < num_offsets; i++) cg[num_literals + i] = len[kNumLit + i];
-  cg[num_literals + num_offsets] = 255;
-  {
-    unsigned char size = cg[0];
+  // generate_codegen (hbw:241-330): serial RLE over <= 316 lengths
+  FB_PFOR(i, 32) S.cgfreq[i] = 0;
+  FB_PFOR(i, num_literals) S.cg[i] = S.len[i];
+  FB_PFOR(i, num_offsets) S.cg[num_literals + i] = S.len[kNumLit + i];
+  FB_WSYNC();
+  if (FB_LANE == 0) {
+    uint8_t *cg = S.cg;
+    uint32_t *cgfreq = S.cgfreq;
+    cg[num_literals + num_offsets] = 255;
+    uint8_t size = cg[0];
     int count = 1, out = 0;
     for (int in = 1; size != 255; in++) {
-      const unsigned char next = cg[in];
+      const uint8_t next = cg[in];
       if (next == size) { count++; continue; }
       if (size != 0) {
         cg[out++] = size; cgfreq[size]++; count--;
         while (count >= 3) {
           const int nn = count < 6 ? count : 6;
-          cg[out++] = 16; cg[out++] = (unsigned char)(nn - 3); cgfreq[16]++; count -= nn;
+          cg[out++] = 16; cg[out++] = (uint8_t)(nn - 3); cgfreq[16]++; count -= nn;
         }
       } else {
         while (count >= 11) {
           const int nn = count < 138 ? count : 138;
-          cg[out++] = 18; cg[out++] = (unsigned char)(nn - 11); cgfreq[18]++; count -= nn;
+          cg[out++] = 18; cg[out++] = (uint8_t)(nn - 11); cgfreq[18]++; count -= nn;
         }
         if (count >= 3) {
-          cg[out++] = 17; cg[out++] = (unsigned char)(count - 3); cgfreq[17]++; count = 0;
+          cg[out++] = 17; cg[out++] = (uint8_t)(count - 3); cgfreq[17]++; count = 0;
         }
       }
       count--;
@@ -249,29 +430,34 @@ FB_HD inline BlockBuild build_block_dev(uint32_t *freq, int kind, uint32_t n, ui
     }
     cg[out] = 255;
   }
-  unsigned char cglen[kNumCodegen];
-  unsigned short cgcode[kNumCodegen];
-  generate_dev(cgfreq, kNumCodegen, 7, cglen, cgcode);
+  FB_WSYNC();
+  warp_generate(S.cgfreq, kNumCodegen, 7, S.cglen, S.cgcode, S);
 
-  // dynamic_size (hbw:335-360)
+  // dynamic_size (hbw:335-360) + payload bits
   const int order[kNumCodegen] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
   int num_codegens = kNumCodegen;
-  while (num_codegens > 4 && cgfreq[order[num_codegens - 1]] == 0) num_codegens--;
-  int size = 3 + 5 + 5 + 4 + 3 * num_codegens + (int)(cgfreq[16] * 2 + cgfreq[17] * 3 + cgfreq[18] * 7);
-  for (int i = 0; i < kNumCodegen; i++) size += (int)cgfreq[i] * cglen[i];
-  uint32_t extra = 0; // extra bits, not part of `size` (callers pass 0)
-  for (int i = 0; i < kNumLit; i++) {
-    size += (int)freq[i] * len[i];
-    if (i >= kLenCodesStart + 8 && i < kLenCodesStart + 28) extra += freq[i] * (uint32_t)((i - kLenCodesStart - 4) >> 2);
-  }
-  if (kind == kKindDynamic) {
-    for (int i = 0; i < kNumDist; i++) {
-      size += (int)freq[kNumLit + i] * len[kNumLit + i];
-      if (i >= 4) extra += freq[kNumLit + i] * (uint32_t)((i - 2) >> 1);
+  while (num_codegens > 4 && S.cgfreq[order[num_codegens - 1]] == 0) num_codegens--;
+  int size = 0;
+  int extra = 0; // extra bits, not part of `size` (callers pass 0)
+  FB_PFOR(i, kNumLit + kNumDist) {
+    if (i < kNumLit) {
+      size += (int)(S.freq[i] * S.len[i]);
+      if (i >= kLenCodesStart + 8 && i < kLenCodesStart + 28) extra += (int)(S.freq[i] * (uint32_t)((i - kLenCodesStart - 4) >> 2));
+    } else if (kind == kKindDynamic) {
+      const int d = i - kNumLit;
+      size += (int)(S.freq[i] * S.len[i]);
+      if (d >= 4) extra += (int)(S.freq[i] * (uint32_t)((d - 2) >> 1));
     }
-  } else {
-    size += 1; // offset_freq[0] (forced to 1, hbw:756) * huff_offset.codes[0].len
   }
+  FB_PFOR(i, kNumCodegen) size += (int)(S.cgfreq[i] * S.cglen[i]);
+  size = wsum(size);
+  extra = wsum(extra);
+  const int data_bits = size - 0; // lit + offset + codegen code bits so far
+  int cg_bits = 0;
+  FB_PFOR(i, kNumCodegen) cg_bits += (int)(S.cgfreq[i] * S.cglen[i]);
+  cg_bits = wsum(cg_bits);
+  if (kind != kKindDynamic) size += 1; // offset_freq[0] (forced to 1, hbw:756) * huff_offset.codes[0].len
+  size += 3 + 5 + 5 + 4 + 3 * num_codegens + (int)(S.cgfreq[16] * 2 + S.cgfreq[17] * 3 + S.cgfreq[18] * 7);
   // "store instead" test (hbw:526-531, :779-784; quirk D2: (size+size)>>4)
   const int ssize = ((int)n + 5) * 8;
   if (ssize < ((size + size) >> 4)) {
@@ -279,32 +465,33 @@ FB_HD inline BlockBuild build_block_dev(uint32_t *freq, int kind, uint32_t n, ui
     return res;
   }
 
-  // write_dynamic_header (hbw:421-471)
-  BitAcc ba;
-  ba.words = hdr_words;
-  ba.acc = 0; ba.nacc = 0; ba.nwords = 0;
-  ba.put(4, 3); // BFINAL = 0, BTYPE = 10
-  ba.put((uint32_t)(num_literals - 257), 5);
-  ba.put((uint32_t)(num_offsets - 1), 5);
-  ba.put((uint32_t)(num_codegens - 4), 4);
-  for (int i = 0; i < num_codegens; i++) ba.put(cglen[order[i]], 3);
-  for (int i = 0;;) {
-    const int cw = cg[i++];
-    if (cw == 255) break;
-    ba.put(cgcode[cw], cglen[cw]);
-    if (cw == 16) ba.put(cg[i++], 2);
-    else if (cw == 17) ba.put(cg[i++], 3);
-    else if (cw == 18) ba.put(cg[i++], 7);
+  // write_dynamic_header (hbw:421-471): serial bit append
+  if (FB_LANE == 0) {
+    BitAcc ba;
+    ba.words = hdr_words;
+    ba.acc = 0; ba.nacc = 0; ba.nwords = 0;
+    ba.put(4, 3); // BFINAL = 0, BTYPE = 10
+    ba.put((uint32_t)(num_literals - 257), 5);
+    ba.put((uint32_t)(num_offsets - 1), 5);
+    ba.put((uint32_t)(num_codegens - 4), 4);
+    for (int i = 0; i < num_codegens; i++) ba.put(S.cglen[order[i]], 3);
+    for (int i = 0;;) {
+      const int cw = S.cg[i++];
+      if (cw == 255) break;
+      ba.put(S.cgcode[cw], S.cglen[cw]);
+      if (cw == 16) ba.put(S.cg[i++], 2);
+      else if (cw == 17) ba.put(S.cg[i++], 3);
+      else if (cw == 18) ba.put(S.cg[i++], 7);
+    }
+    S.misc[0] = ba.finish();
   }
-  const int hdr_bits = ba.finish();
+  FB_WSYNC();
+  const int hdr_bits = S.misc[0];
   res.hdr_nbits = (uint32_t)hdr_bits;
   // total bits of the block = header + sum(freq*len) + extra bits
-  uint32_t data_bits = extra;
-  for (int i = 0; i < kNumLit; i++) data_bits += freq[i] * len[i];
-  if (kind == kKindDynamic)
-    for (int i = 0; i < kNumDist; i++) data_bits += freq[kNumLit + i] * len[kNumLit + i];
-  res.blk_bits = (uint32_t)hdr_bits + data_bits;
-  for (int i = 0; i < kNumLit + kNumDist; i++) codeout[i] = (uint32_t)code[i] | ((uint32_t)len[i] << 16);
+  res.blk_bits = (uint32_t)(hdr_bits + (data_bits - cg_bits) + extra);
+  FB_PFOR(i, kNumLit + kNumDist) codeout[i] = (uint32_t)S.code[i] | ((uint32_t)S.len[i] << 16);
+  FB_WSYNC();
   return res;
 }
 

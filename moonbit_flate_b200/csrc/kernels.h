@@ -48,7 +48,7 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st);
 void launch_histogram(const DeflateJob &j, cudaStream_t st);
 // K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,
 //     huffman-bit-writer.mbt:241-471)
-void launch_build_codes(const DeflateJob &j, cudaStream_t st);
+void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st);
 // layout: per-stream bit offsets, stream sizes, output offsets
 void launch_layout(const DeflateJob &j, cudaStream_t st);
 // K4: bit packing (huffman-bit-writer.mbt:596-824, :474-487) + stream trailers
@@ -58,6 +58,9 @@ void launch_pack(const DeflateJob &j, cudaStream_t st);
 void launch_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n, cudaStream_t st);
 // fixed-size segment offsets: off[i] = min(i*seg, n), i in [0, nseg]
 void launch_fill_seg_off(uint64_t *off, uint64_t nseg, uint64_t seg, uint64_t n, cudaStream_t st);
+
+// out[i] = in[i] + delta (mod 2^64), i in [0, cnt): re-bases offset arrays for chunked host calls
+void launch_affine_u64(uint64_t *out, const uint64_t *in, uint64_t cnt, uint64_t delta, cudaStream_t st);
 
 struct InflateJob {
   const uint8_t *comp;

@@ -452,6 +452,18 @@ void launch_fill_seg_off(uint64_t *off, uint64_t nseg, uint64_t seg, uint64_t n,
   k_fill_seg_off<<<g, 256, 0, st>>>(off, nseg, seg, n);
 }
 
+__global__ void k_affine_u64(uint64_t *out, const uint64_t *in, uint64_t cnt, uint64_t delta)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) out[i] = in[i] + delta;
+}
+
+void launch_affine_u64(uint64_t *out, const uint64_t *in, uint64_t cnt, uint64_t delta, cudaStream_t st)
+{
+  if (cnt == 0) return;
+  k_affine_u64<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(out, in, cnt, delta);
+}
+
 // Single-CTA exclusive scan (metadata only: <= a few million entries).
 __global__ void __launch_bounds__(1024) k_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n)
 {

@@ -17,13 +17,15 @@ using namespace fb;
 
 extern "C" void fbm_generate(const uint32_t *freq, int nsym, int max_bits, uint8_t *len, uint16_t *code)
 {
-  generate_dev(freq, nsym, max_bits, len, code);
+  static HuffScratch S;
+  warp_generate(freq, nsym, max_bits, len, code, S);
 }
 
 extern "C" int fbm_build_block(uint32_t *freq, int kind, uint32_t n, uint32_t *codeout, uint32_t *hdr_words,
                                uint32_t *hdr_nbits, uint32_t *blk_bits)
 {
-  BlockBuild r = build_block_dev(freq, kind, n, codeout, hdr_words);
+  static HuffScratch S;
+  BlockBuild r = build_block_warp(freq, kind, n, codeout, hdr_words, S);
   *hdr_nbits = r.hdr_nbits;
   *blk_bits = r.blk_bits;
   return r.kind;

@@ -10,6 +10,16 @@ from helpers import BLK_DYNAMIC, Corpus, Oracle
 pytestmark = pytest.mark.gpu
 
 
+def C_u64():
+    import ctypes
+    return ctypes.c_uint64()
+
+
+def need_addr(v):
+    import ctypes
+    return ctypes.addressof(v)
+
+
 @pytest.fixture(scope="module")
 def ctx():
     import moonbit_flate_b200 as fb
@@ -230,3 +240,43 @@ def test_writer_dict_kat(ctx):
     assert w.write(b"hello again world") == (17, None)
     assert w.close() is None
     assert b1.getvalue() == want
+
+
+def test_host_api_chunk_pipeline(oracle, corpus, monkeypatch):
+    """The host-buffer entry points cut a batch into chunks of whole streams and pipeline H2D / kernels / D2H;
+    chunking must not change a byte.  Forced here with 1 MiB chunks over ragged stream sizes."""
+    import moonbit_flate_b200 as fb
+
+    monkeypatch.setenv("FB200_CHUNK_MB", "1")
+    c = fb.Context()
+    monkeypatch.delenv("FB200_CHUNK_MB")
+    try:
+        rng = np.random.default_rng(8)
+        sizes = [int(x) for x in rng.integers(0, 300000, 40)] + [0, 1, 65536, 65536, 2_500_000]
+        datas = [corpus.unit(n, seed=31, index=i, klass=i % 6) for i, n in enumerate(sizes)]
+        src = np.frombuffer(b"".join(datas), dtype=np.uint8)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        comp, doff = c.deflate_streams(src, off)
+        assert int(doff[-1]) == comp.size
+        for i in (0, 1, 2, 17, 39, 40, 41, 42, 43, 44):
+            assert comp[int(doff[i]): int(doff[i + 1])].tobytes() == oracle.deflate(datas[i]), i
+        ooff = np.concatenate([[0], np.cumsum([n + 5 for n in sizes])]).astype(np.uint64)
+        out, olen, st, eo, cons = c.inflate_batch(comp, doff, ooff)
+        assert (st == 0).all() and list(olen) == sizes
+        for i, d in enumerate(datas):
+            assert out[int(ooff[i]): int(ooff[i]) + len(d)].tobytes() == d, i
+            assert int(cons[i]) == int(doff[i + 1] - doff[i])
+        # fixed-size segments with a ragged tail, several chunks
+        seg = corpus.fill(70, 65536, seed=33)[: 69 * 65536 + 123]
+        comp2, off2 = c.deflate_segments(seg, 65536)
+        for i in (0, 15, 16, 17, 68, 69):
+            assert comp2[int(off2[i]): int(off2[i + 1])].tobytes() == oracle.deflate(seg[i * 65536:(i + 1) * 65536].tobytes())
+        # capacity error reports the size the call needs
+        need = C_u64()
+        small = np.empty(1000, np.uint8)
+        so = np.zeros(71, np.uint64)
+        rc = fb._lib.fb200_deflate_segments(c._h, seg.ctypes.data, seg.size, 65536, small.ctypes.data, small.size,
+                                            so.ctypes.data, need_addr(need))
+        assert rc == fb.ERR_DST_TOO_SMALL and need.value == comp2.size
+    finally:
+        c.close()

@@ -73,6 +73,34 @@ def test_generate_matches_oracle(hm, oracle):
             assert gl.max(initial=0) <= mb
 
 
+def test_generate_tie_heavy_randomized(hm, oracle):
+    """The eager, level-by-level package-merge of huff_build.cuh against the reference's lazy boundary
+    package-merge on tie-heavy frequency vectors (tie-breaking decides the bit counts)."""
+    rng = np.random.default_rng(12345)
+    for it in range(3000):
+        n = int(rng.choice([19, 30, 286]))
+        mode = it % 6
+        if mode == 0:
+            f = rng.integers(0, 3, n)
+        elif mode == 1:
+            f = rng.integers(0, 8, n)
+        elif mode == 2:
+            f = (rng.geometric(0.3, n) - 1) * rng.integers(1, 4)
+        elif mode == 3:
+            f = (2 ** rng.integers(0, 16, n)) * (rng.random(n) < 0.6)
+        elif mode == 4:
+            f = np.minimum((rng.pareto(0.5, n) * 3).astype(np.int64), 65535)
+        else:
+            k = int(rng.integers(3, n + 1))
+            f = np.zeros(n, np.int64)
+            f[rng.choice(n, k, replace=False)] = rng.integers(1, 5, k)
+        f = np.asarray(f, np.int64)
+        mb = 7 if n == 19 and it % 2 else 15
+        gl, gc = hm.generate(f, mb)
+        ol, oc = oracle.huff_generate(f, mb)
+        assert np.array_equal(gl, ol) and np.array_equal(gc, oc), (f.tolist(), mb)
+
+
 SIZES = [128, 129, 300, 4096, 30000, 65534, 65535, 65536, 65662, 65663, 70000, 131070, 200000]
 
 
