@@ -63,7 +63,8 @@ struct fb200_ctx {
   DevBuf h_src_off; // fixed-size segment offsets of the *_segments_dev entry point
   DevBuf p_in[2], p_out[2], p_off_in[2], p_off_out[2], p_off_abs[2], p_len[2], p_status[2], p_eoff[2], p_cons[2];
   DevBuf all_off, all_off2;
-  DevBuf i_fallback;
+  DevBuf i_fallback, i_rec_off, i_nrec, i_records, i_order, i_order_hist;
+  bool inflate_v1 = true; // FB200_INFLATE_V1=0 selects the experimental thread-per-stream path (inflate2.cu)
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t e_in[2] = {}, e_comp[2] = {}, e_out[2] = {};
   uint64_t chunk_bytes = 128ull << 20;
@@ -136,6 +137,7 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
     cudaEventCreateWithFlags(&ctx->e_comp[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->e_out[i], cudaEventDisableTiming);
   }
+  if (const char *e = getenv("FB200_INFLATE_V1")) ctx->inflate_v1 = atoi(e) != 0;
   if (const char *e = getenv("FB200_CHUNK_MB")) {
     const long mb = atol(e);
     if (mb > 0) ctx->chunk_bytes = (uint64_t)mb << 20;
@@ -157,7 +159,7 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
   DevBuf *all[] = {&ctx->stream_blk0, &ctx->stream_bytes, &ctx->stream_trailer, &ctx->dst_off_own, &ctx->blk_stream,
                    &ctx->blk_ntok, &ctx->blk_kind, &ctx->blk_bits, &ctx->blk_bit_start, &ctx->blk_hdr_nbits,
                    &ctx->blk_hdr, &ctx->blk_freq, &ctx->blk_code, &ctx->tokens, &ctx->counters, &ctx->h_src_off,
-                   &ctx->all_off, &ctx->all_off2, &ctx->i_fallback};
+                   &ctx->all_off, &ctx->all_off2, &ctx->i_fallback, &ctx->i_rec_off, &ctx->i_nrec, &ctx->i_records, &ctx->i_order, &ctx->i_order_hist};
   for (int i = 0; i < 2; i++) {
     DevBuf *slot[] = {&ctx->p_in[i], &ctx->p_out[i], &ctx->p_off_in[i], &ctx->p_off_out[i], &ctx->p_off_abs[i],
                       &ctx->p_len[i], &ctx->p_status[i], &ctx->p_eoff[i], &ctx->p_cons[i]};
@@ -555,14 +557,34 @@ extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, co
   j.counters = ctx->counters.as<uint32_t>();
   j.fallback = ctx->i_fallback.as<uint32_t>();
   for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
+  uint64_t launches = nstreams ? 2 : 0;
+  if (!ctx->inflate_v1 && nstreams) {
+    // record areas: sized from the output capacity (two u64 read back; a match yields >= 3 bytes)
+    CK(cudaMemcpyAsync(ctx->pinned, d_out_off, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->pinned + 1, d_out_off + nstreams, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t cap_total = ctx->pinned[1] - ctx->pinned[0];
+    CK(ctx->i_rec_off.ensure((nstreams + 1) * 8));
+    CK(ctx->i_nrec.ensure((nstreams + 1) * 4));
+    CK(ctx->i_records.ensure((cap_total / 3 + 4 * nstreams + 8) * 8));
+    j.rec_off = ctx->i_rec_off.as<uint64_t>();
+    j.nrec = ctx->i_nrec.as<uint32_t>();
+    j.records = ctx->i_records.as<uint2>();
+    CK(ctx->i_order.ensure((nstreams + 1) * 4));
+    CK(ctx->i_order_hist.ensure(1024 * 4));
+    j.order = ctx->i_order.as<uint32_t>();
+    launch_rec_off(d_out_off, ctx->i_rec_off.as<uint64_t>(), nstreams, st);
+    launches += 5;
+  }
   ctx->stage_begin(FB200_STAGE_INFLATE);
-  launch_inflate(j, ctx->num_sms, st);
+  if (!ctx->inflate_v1) launch_inflate2(j, ctx->num_sms, ctx->i_order_hist.as<uint32_t>(), st);
+  launch_inflate(j, ctx->num_sms, ctx->inflate_v1, st);
   ctx->stage_end(FB200_STAGE_INFLATE);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->pinned, j.counters, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   ctx->stats = fb200_stats{};
-  ctx->stats.kernel_launches = nstreams ? 2 : 0;
+  ctx->stats.kernel_launches = launches;
   ctx->stats.inflate_fallbacks = reinterpret_cast<const uint32_t *>(ctx->pinned)[2];
   return FB200_OK;
 }

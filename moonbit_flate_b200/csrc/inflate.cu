@@ -831,9 +831,13 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(InflateJob j)
   }
 }
 
-void launch_inflate(const InflateJob &j, int num_sms, cudaStream_t st)
+void launch_inflate(const InflateJob &j, int num_sms, bool fast_v1, cudaStream_t st)
 {
   if (j.nstreams == 0) return;
+  if (!fast_v1) {
+    k_inflate<<<(unsigned)num_sms * 2, kInflateWarps * 32, 0, st>>>(j);
+    return;
+  }
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     const char *e = getenv("FB200_INFLATE_CTAS");

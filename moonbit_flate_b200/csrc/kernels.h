@@ -73,9 +73,19 @@ struct InflateJob {
   int64_t *err_off;         // [nstreams]
   uint64_t *consumed;       // [nstreams] or null
   uint32_t *fallback;       // [nstreams] streams the fast path hands to the exact kernel
-  uint32_t *counters;       // [0] fast work counter, [1] exact work counter, [2] fallback count
+  uint32_t *counters;       // [0] fast work counter, [1] exact work counter, [2] fallback count, [3] copy work counter
+  // two-kernel fast path (inflate2.cu): recorded back-references
+  uint2 *records;           // {dst, len | (dist-1) << 16}
+  const uint64_t *rec_off;  // [nstreams+1] record area of each stream
+  uint32_t *nrec;           // [nstreams] records written (0: nothing to copy, or stream handed to the exact kernel)
+  const uint32_t *order;    // [nstreams] decode order (largest compressed size first)
 };
-// K6: batched inflate, one warp per stream (inflate.mbt, dict-decoder.mbt)
-void launch_inflate(const InflateJob &j, int num_sms, cudaStream_t st);
+// K6: batched inflate.  fast_v1: warp-per-stream fast kernel (inflate.cu); otherwise the caller has run
+// launch_inflate2 and only the exact kernel runs here, over the fallback list.
+void launch_inflate(const InflateJob &j, int num_sms, bool fast_v1, cudaStream_t st);
+// thread-per-stream decode + warp-per-stream copy replay (inflate2.cu)
+// order_hist: device scratch of 1024 uint32
+void launch_inflate2(const InflateJob &j, int num_sms, uint32_t *order_hist, cudaStream_t st);
+void launch_rec_off(const uint64_t *out_off, uint64_t *rec_off, uint64_t ns, cudaStream_t st);
 
 } // namespace fb
