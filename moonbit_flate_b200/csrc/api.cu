@@ -11,6 +11,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -64,10 +65,17 @@ struct fb200_ctx {
   DevBuf p_in[2], p_out[2], p_off_in[2], p_off_out[2], p_off_abs[2], p_len[2], p_status[2], p_eoff[2], p_cons[2];
   DevBuf all_off, all_off2;
   DevBuf i_fallback, i_rec_off, i_nrec, i_records, i_order, i_order_hist;
-  bool inflate_v1 = true; // FB200_INFLATE_V1=0 selects the experimental thread-per-stream path (inflate2.cu)
+  // fast path of the inflate: 3 = warp per stream, lanes decode a block in parallel (inflate3.cu, default);
+  // 1 = warp per stream, warp-uniform decode (inflate.cu); 2 = thread per stream (inflate2.cu, experimental)
+  int inflate_mode = 3;
+  uint32_t *d_wm = nullptr;        // [2] arrival watermarks (deflate, inflate) advanced by the H2D stream
+  uint32_t *wm_vals = nullptr;     // pinned: the values the H2D stream copies into d_wm, one per chunk
+  volatile uint32_t *h_flags = nullptr; // mapped pinned: inflate output groups finished on the device
+  DevBuf group_done;
+  static constexpr int kMaxChunks = 4096;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t e_in[2] = {}, e_comp[2] = {}, e_out[2] = {};
-  uint64_t chunk_bytes = 128ull << 20;
+  uint64_t chunk_bytes = 32ull << 20;
   uint64_t *pinned = nullptr; // small pinned read-back area
   // last deflate job (for introspection)
   DeflateJob last{};
@@ -137,11 +145,23 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
     cudaEventCreateWithFlags(&ctx->e_comp[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->e_out[i], cudaEventDisableTiming);
   }
-  if (const char *e = getenv("FB200_INFLATE_V1")) ctx->inflate_v1 = atoi(e) != 0;
+  cudaMalloc((void **)&ctx->d_wm, 64);
+  cudaMallocHost((void **)&ctx->wm_vals, fb200_ctx::kMaxChunks * sizeof(uint32_t));
+  cudaHostAlloc((void **)&ctx->h_flags, fb200_ctx::kMaxChunks * sizeof(uint32_t), cudaHostAllocMapped);
+  if (!ctx->d_wm || !ctx->wm_vals || !ctx->h_flags) { cudaGetLastError(); fb200_destroy(ctx); return FB200_ERR_CUDA; }
+  if (const char *e = getenv("FB200_INFLATE_MODE")) {
+    const int m = atoi(e);
+    if (m >= 1 && m <= 3) ctx->inflate_mode = m;
+  }
   if (const char *e = getenv("FB200_CHUNK_MB")) {
     const long mb = atol(e);
     if (mb > 0) ctx->chunk_bytes = (uint64_t)mb << 20;
   }
+  preload_parse_kernels();
+  preload_encode_kernels();
+  preload_inflate_kernels();
+  preload_inflate2_kernels();
+  preload_inflate3_kernels();
   launch_init_tables(ctx->stream);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
     delete ctx;
@@ -168,6 +188,10 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
     if (ctx->e_comp[i]) cudaEventDestroy(ctx->e_comp[i]);
     if (ctx->e_out[i]) cudaEventDestroy(ctx->e_out[i]);
   }
+  ctx->group_done.release();
+  if (ctx->d_wm) cudaFree(ctx->d_wm);
+  if (ctx->wm_vals) cudaFreeHost(ctx->wm_vals);
+  if (ctx->h_flags) cudaFreeHost((void *)ctx->h_flags);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   for (DevBuf *b : all) b->release();
@@ -203,8 +227,10 @@ extern "C" uint64_t fb200_frame_header_bytes(uint64_t nseg) { return 16 + 4 * ns
 // deflate core: phase A = everything up to the output layout (returns the
 // total compressed size), phase B = bit packing into d_dst.
 
-static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t *d_src_off, uint64_t ns,
-                           uint64_t n_total, uint64_t *d_dst_off, uint64_t *total_out)
+// nb_known: number of blocks if the caller knows it (host-side offsets), ~0 to read it back from the device.
+// avail: arrival watermark for host-buffer calls (see DeflateJob::avail), or null.
+static int deflate_phase_a_launch(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t *d_src_off, uint64_t ns,
+                                  uint64_t n_total, uint64_t *d_dst_off, uint64_t nb_known, const uint32_t *avail)
 {
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -224,6 +250,7 @@ static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
   j.stream_trailer_bit = ctx->stream_trailer.as<uint64_t>();
   j.dst_off = d_dst_off;
   j.counters = ctx->counters.as<uint32_t>();
+  j.avail = avail;
   CK(cudaMemsetAsync(j.counters, 0, 64, st));
   uint64_t launches = 0;
   for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
@@ -232,9 +259,12 @@ static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
   launch_count_blocks(j, st);
   launch_scan_u64(j.stream_blk0, j.stream_blk0, ns, st);
   launches += 2;
-  CK(cudaMemcpyAsync(ctx->pinned, j.stream_blk0 + ns, 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  const uint64_t nb = ctx->pinned[0];
+  uint64_t nb = nb_known;
+  if (nb == ~0ull) {
+    CK(cudaMemcpyAsync(ctx->pinned, j.stream_blk0 + ns, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nb = ctx->pinned[0];
+  }
   if (nb > 0x7fffffffull) { ctx->err = "too many blocks in one call"; return FB200_ERR_ARG; }
   j.nblocks = nb;
   const uint64_t nbp = nb + 1;
@@ -280,11 +310,24 @@ static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t 
   launches += 7;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->pinned, j.dst_off + ns, 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  *total_out = ctx->pinned[0];
   ctx->stats.nblocks = nb;
   ctx->stats.kernel_launches = launches;
   return FB200_OK;
+}
+
+static int deflate_phase_a_finish(fb200_ctx *ctx, uint64_t *total_out)
+{
+  CK(cudaStreamSynchronize(ctx->stream));
+  *total_out = ctx->pinned[0];
+  return FB200_OK;
+}
+
+static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t *d_src_off, uint64_t ns,
+                           uint64_t n_total, uint64_t *d_dst_off, uint64_t *total_out)
+{
+  int rc = deflate_phase_a_launch(ctx, d_src, d_src_off, ns, n_total, d_dst_off, ~0ull, nullptr);
+  if (rc != FB200_OK) return rc;
+  return deflate_phase_a_finish(ctx, total_out);
 }
 
 static int deflate_phase_b(fb200_ctx *ctx, uint8_t *d_dst, uint64_t total)
@@ -336,15 +379,10 @@ extern "C" int fb200_deflate_segments_dev(fb200_ctx *ctx, const uint8_t *d_src, 
   return rc;
 }
 
-// Host-buffer deflate: the batch is cut into chunks of whole streams (~chunk_bytes each) that flow
-// through a two-slot pipeline -- H2D of chunk c+1 (stream s_in) and D2H of chunk c-1 (s_out) run
-// beside the kernels of chunk c (ctx->stream).  Streams are independent, so chunking never changes
-// a byte; offsets are re-based per chunk on the device.
-struct HostChunk {
-  uint64_t a, b;        // streams [a, b)
-  uint64_t byte0, bytes; // source byte range
-};
-
+// Host-buffer deflate.  The kernels are launched once for the whole batch; the input is copied in chunks
+// on a second stream, and after every chunk that stream advances a device watermark ("streams whose bytes
+// have arrived") which the parse waits on, so the H2D copy runs beside the parse instead of in front of it.
+// Chunk boundaries are rounded up to 128 bytes: a cache line never holds bytes of two different arrivals.
 static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, const uint64_t *src_off, uint64_t ns,
                                uint64_t seg_size, uint8_t *dst, uint64_t dst_cap, uint64_t *dst_off, uint64_t *out_len)
 {
@@ -357,99 +395,82 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
     ctx->last = DeflateJob{};
     return FB200_OK;
   }
-  std::vector<HostChunk> chunks;
-  {
-    uint64_t a = 0;
-    while (a < ns) {
-      uint64_t b = a;
-      const uint64_t byte0 = src_off ? src_off[a] : a * seg_size;
-      uint64_t bytes = 0;
-      if (src_off) {
-        while (b < ns && (b == a || bytes < ctx->chunk_bytes)) { b++; bytes = src_off[b] - byte0; }
-      } else {
-        uint64_t cnt = ctx->chunk_bytes / seg_size;
-        if (cnt == 0) cnt = 1;
-        b = a + cnt < ns ? a + cnt : ns;
-        const uint64_t end = b * seg_size < n ? b * seg_size : n;
-        bytes = end - byte0;
+  if (ns > 0xfffffff0ull) { ctx->err = "too many streams"; return FB200_ERR_ARG; }
+  const uint64_t base0 = src_off ? src_off[0] : 0; // streams may start anywhere in src
+  // chunks of whole streams + number of blocks (deflate.mbt:222-229: one block per 65535 bytes)
+  struct Cut { uint64_t streams, bytes; }; // streams / bytes delivered once this chunk has arrived
+  std::vector<Cut> cuts;
+  uint64_t nb = 0;
+  uint64_t step = ctx->chunk_bytes;
+  if (n / step + 2 > (uint64_t)fb200_ctx::kMaxChunks) step = n / (fb200_ctx::kMaxChunks - 2) + 1;
+  if (src_off) {
+    uint64_t next_cut = step;
+    for (uint64_t i = 0; i < ns; i++) {
+      const uint64_t len = src_off[i + 1] - src_off[i];
+      nb += (len + kBlockSize - 1) / kBlockSize;
+      const uint64_t endb = src_off[i + 1] - base0;
+      if (endb >= next_cut || i + 1 == ns) {
+        cuts.push_back({i + 1, endb});
+        next_cut = endb + step;
       }
-      chunks.push_back({a, b, byte0, bytes});
-      a = b;
     }
+  } else {
+    uint64_t per = step / seg_size;
+    if (per == 0) per = 1;
+    for (uint64_t a = 0; a < ns; a += per) {
+      const uint64_t b = a + per < ns ? a + per : ns;
+      cuts.push_back({b, b * seg_size < n ? b * seg_size : n});
+    }
+    const uint64_t full = n / seg_size, tail = n % seg_size;
+    nb = full * ((seg_size + kBlockSize - 1) / kBlockSize) + (tail + kBlockSize - 1) / kBlockSize;
   }
-  uint64_t max_bytes = 0, max_cnt = 0;
-  for (const HostChunk &c : chunks) {
-    if (c.bytes > max_bytes) max_bytes = c.bytes;
-    if (c.b - c.a > max_cnt) max_cnt = c.b - c.a;
-  }
-  for (int i = 0; i < 2; i++) {
-    CK(ctx->p_in[i].ensure(max_bytes + 16));
-    CK(ctx->p_off_in[i].ensure((max_cnt + 1) * 8));
-    CK(ctx->p_off_out[i].ensure((max_cnt + 1) * 8));
-    CK(ctx->p_off_abs[i].ensure((max_cnt + 1) * 8));
-    if (chunks.size() > 1) CK(ctx->p_out[i].ensure(max_bytes / 2 + max_bytes / 8 + (1u << 20))); // grows if needed
-  }
+  CK(ctx->p_in[0].ensure(n + 256));
+  CK(ctx->p_off_in[0].ensure((ns + 1) * 8));
+  CK(ctx->p_off_out[0].ensure((ns + 1) * 8));
+  uint8_t *d_src = ctx->p_in[0].as<uint8_t>();
+  uint64_t *d_off = ctx->p_off_in[0].as<uint64_t>();
+  // reset the watermark before the H2D stream may touch it
+  CK(cudaMemsetAsync(ctx->d_wm, 0, 8, st));
+  CK(cudaEventRecord(ctx->e_comp[0], st));
+  CK(cudaStreamWaitEvent(ctx->s_in, ctx->e_comp[0], 0));
   if (src_off) {
     CK(ctx->all_off.ensure((ns + 1) * 8));
     CK(cudaMemcpyAsync(ctx->all_off.p, src_off, (ns + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    CK(cudaEventRecord(ctx->e_in[0], ctx->s_in));
+    CK(cudaStreamWaitEvent(st, ctx->e_in[0], 0));
+    launch_affine_u64(d_off, ctx->all_off.as<uint64_t>(), ns + 1, 0ull - base0, st);
+  } else {
+    launch_fill_seg_off(d_off, ns, seg_size, n, st);
   }
-  auto issue_h2d = [&](size_t c) -> int {
-    const HostChunk &ch = chunks[c];
-    const int slot = (int)(c & 1);
-    if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ctx->e_comp[slot], 0));
-    if (ch.bytes) CK(cudaMemcpyAsync(ctx->p_in[slot].p, src + ch.byte0, ch.bytes, cudaMemcpyHostToDevice, ctx->s_in));
-    if (src_off)
-      launch_affine_u64(ctx->p_off_in[slot].as<uint64_t>(), ctx->all_off.as<uint64_t>() + ch.a, ch.b - ch.a + 1,
-                        0ull - ch.byte0, ctx->s_in);
-    else
-      launch_fill_seg_off(ctx->p_off_in[slot].as<uint64_t>(), ch.b - ch.a, seg_size, ch.bytes, ctx->s_in);
-    CK(cudaEventRecord(ctx->e_in[slot], ctx->s_in));
-    return FB200_OK;
-  };
-  int rc = issue_h2d(0);
+  int rc = deflate_phase_a_launch(ctx, d_src, d_off, ns, n, ctx->p_off_out[0].as<uint64_t>(), nb, ctx->d_wm);
   if (rc != FB200_OK) return rc;
-  uint64_t base = 0, nblocks = 0, launches = 0;
-  bool overflow = false;
-  for (size_t c = 0; c < chunks.size(); c++) {
-    const HostChunk &ch = chunks[c];
-    const int slot = (int)(c & 1);
-    if (c + 1 < chunks.size() && (rc = issue_h2d(c + 1)) != FB200_OK) return rc;
-    CK(cudaStreamWaitEvent(st, ctx->e_in[slot], 0));
-    uint64_t total = 0;
-    rc = deflate_phase_a(ctx, ctx->p_in[slot].as<uint8_t>(), ctx->p_off_in[slot].as<uint64_t>(), ch.b - ch.a, ch.bytes,
-                         ctx->p_off_out[slot].as<uint64_t>(), &total);
-    if (rc != FB200_OK) return rc;
-    nblocks += ctx->stats.nblocks;
-    launches += ctx->stats.kernel_launches + 2;
-    if (base + total > dst_cap) overflow = true;
-    if (!overflow) {
-      if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->e_out[slot], 0));
-      CK(ctx->p_out[slot].ensure(total + 16));
-      rc = deflate_phase_b(ctx, ctx->p_out[slot].as<uint8_t>(), total);
-      if (rc != FB200_OK) return rc;
-      launches += 2;
-      if (dst_off)
-        launch_affine_u64(ctx->p_off_abs[slot].as<uint64_t>(), ctx->p_off_out[slot].as<uint64_t>(), ch.b - ch.a + 1,
-                          base, st);
-      CK(cudaEventRecord(ctx->e_comp[slot], st));
-      CK(cudaStreamWaitEvent(ctx->s_out, ctx->e_comp[slot], 0));
-      if (total) CK(cudaMemcpyAsync(dst + base, ctx->p_out[slot].p, total, cudaMemcpyDeviceToHost, ctx->s_out));
-      if (dst_off)
-        CK(cudaMemcpyAsync(dst_off + ch.a, ctx->p_off_abs[slot].p, (ch.b - ch.a + 1) * 8, cudaMemcpyDeviceToHost,
-                           ctx->s_out));
-      CK(cudaEventRecord(ctx->e_out[slot], ctx->s_out));
-    } else {
-      CK(cudaEventRecord(ctx->e_comp[slot], st));
+  // the kernels are queued; now feed them
+  {
+    uint64_t done = 0;
+    for (size_t c = 0; c < cuts.size(); c++) {
+      uint64_t upto = c + 1 == cuts.size() ? n : ((cuts[c].bytes + 127) & ~127ull);
+      if (upto > n) upto = n;
+      if (upto > done) {
+        CK(cudaMemcpyAsync(d_src + done, src + base0 + done, upto - done, cudaMemcpyHostToDevice, ctx->s_in));
+        done = upto;
+      }
+      ctx->wm_vals[c] = (uint32_t)cuts[c].streams;
+      CK(cudaMemcpyAsync(ctx->d_wm, &ctx->wm_vals[c], 4, cudaMemcpyHostToDevice, ctx->s_in));
     }
-    base += total;
   }
-  CK(cudaStreamSynchronize(ctx->s_in));
-  CK(cudaStreamSynchronize(ctx->s_out));
+  uint64_t total = 0;
+  rc = deflate_phase_a_finish(ctx, &total);
+  if (rc != FB200_OK) return rc;
+  *out_len = total;
+  if (total > dst_cap) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
+  CK(ctx->p_out[0].ensure(total + 16));
+  rc = deflate_phase_b(ctx, ctx->p_out[0].as<uint8_t>(), total);
+  if (rc != FB200_OK) return rc;
+  if (total) CK(cudaMemcpyAsync(dst, ctx->p_out[0].p, total, cudaMemcpyDeviceToHost, st));
+  if (dst_off) CK(cudaMemcpyAsync(dst_off, ctx->p_off_out[0].p, (ns + 1) * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  *out_len = base; // on overflow: the capacity the call needs
-  ctx->stats.nblocks = nblocks;
-  ctx->stats.kernel_launches = launches;
-  if (overflow) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
+  CK(cudaStreamSynchronize(ctx->s_in));
+  ctx->stats.kernel_launches += 3;
   return FB200_OK;
 }
 
@@ -532,12 +553,17 @@ extern "C" int fb200_last_blocks(const fb200_ctx *cctx, uint32_t *blk_ntok, uint
 // ------------------------------------------------------------------
 // inflate
 
-extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t *d_comp_off,
-                                       uint64_t nstreams, uint8_t *d_out, const uint64_t *d_out_off,
-                                       uint64_t *d_out_len, int32_t *d_status, int64_t *d_err_off,
-                                       uint64_t *d_consumed)
+struct InflateHooks { // host-buffer calls only
+  const uint32_t *avail = nullptr;
+  uint32_t *group_done = nullptr;
+  volatile uint32_t *group_flag = nullptr;
+  uint32_t group_streams = 0;
+};
+
+static int inflate_launch(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t *d_comp_off, uint64_t nstreams,
+                          uint8_t *d_out, const uint64_t *d_out_off, uint64_t *d_out_len, int32_t *d_status,
+                          int64_t *d_err_off, uint64_t *d_consumed, uint64_t cap_total_known, const InflateHooks &hk)
 {
-  if (!ctx || !d_comp_off || !d_out_off || !d_out_len || !d_status || !d_err_off) return FB200_ERR_ARG;
   if (nstreams > 0xfffffff0ull) return FB200_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -556,14 +582,23 @@ extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, co
   j.consumed = d_consumed;
   j.counters = ctx->counters.as<uint32_t>();
   j.fallback = ctx->i_fallback.as<uint32_t>();
+  j.avail = hk.avail;
+  j.group_done = hk.group_done;
+  j.group_flag = hk.group_flag;
+  j.group_streams = hk.group_streams;
   for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
   uint64_t launches = nstreams ? 2 : 0;
-  if (!ctx->inflate_v1 && nstreams) {
-    // record areas: sized from the output capacity (two u64 read back; a match yields >= 3 bytes)
-    CK(cudaMemcpyAsync(ctx->pinned, d_out_off, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ctx->pinned + 1, d_out_off + nstreams, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const uint64_t cap_total = ctx->pinned[1] - ctx->pinned[0];
+  int mode = ctx->inflate_mode;
+  if (mode == 2 && hk.avail) mode = 3; // the overlapped host path is wired into modes 1 and 3
+  if (mode != 1 && nstreams) {
+    // record areas: sized from the output capacity (a match yields >= 3 bytes)
+    uint64_t cap_total = cap_total_known;
+    if (cap_total == ~0ull) {
+      CK(cudaMemcpyAsync(ctx->pinned, d_out_off, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->pinned + 1, d_out_off + nstreams, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      cap_total = ctx->pinned[1] - ctx->pinned[0];
+    }
     CK(ctx->i_rec_off.ensure((nstreams + 1) * 8));
     CK(ctx->i_nrec.ensure((nstreams + 1) * 4));
     CK(ctx->i_records.ensure((cap_total / 3 + 4 * nstreams + 8) * 8));
@@ -574,21 +609,51 @@ extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, co
     CK(ctx->i_order_hist.ensure(1024 * 4));
     j.order = ctx->i_order.as<uint32_t>();
     launch_rec_off(d_out_off, ctx->i_rec_off.as<uint64_t>(), nstreams, st);
-    launches += 5;
+    launches += mode == 2 ? 5 : 1;
+    if (mode == 3) {
+      // longest streams first -- unless a host-buffer call wants output groups to finish in index order
+      if (hk.avail) j.order = nullptr;
+      else { launch_stream_order(j, ctx->i_order_hist.as<uint32_t>(), st); launches += 3; }
+    }
   }
   ctx->stage_begin(FB200_STAGE_INFLATE);
-  if (!ctx->inflate_v1) launch_inflate2(j, ctx->num_sms, ctx->i_order_hist.as<uint32_t>(), st);
-  launch_inflate(j, ctx->num_sms, ctx->inflate_v1, st);
+  if (mode == 2) launch_inflate2(j, ctx->num_sms, ctx->i_order_hist.as<uint32_t>(), st);
+  else if (mode == 3) launch_inflate3(j, ctx->num_sms, st);
+  launch_inflate(j, ctx->num_sms, mode == 1, st);
   ctx->stage_end(FB200_STAGE_INFLATE);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->pinned, j.counters, 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
   ctx->stats = fb200_stats{};
   ctx->stats.kernel_launches = launches;
-  ctx->stats.inflate_fallbacks = reinterpret_cast<const uint32_t *>(ctx->pinned)[2];
   return FB200_OK;
 }
 
+static int inflate_finish(fb200_ctx *ctx)
+{
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.inflate_fallbacks = reinterpret_cast<const uint32_t *>(ctx->pinned)[2];
+  if (getenv("FB200_TRACE"))
+    fprintf(stderr, "[fb200] inflate: rounds=%u blocks=%u\n", reinterpret_cast<const uint32_t *>(ctx->pinned)[5],
+            reinterpret_cast<const uint32_t *>(ctx->pinned)[6]);
+  return FB200_OK;
+}
+
+extern "C" int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t *d_comp_off,
+                                       uint64_t nstreams, uint8_t *d_out, const uint64_t *d_out_off,
+                                       uint64_t *d_out_len, int32_t *d_status, int64_t *d_err_off,
+                                       uint64_t *d_consumed)
+{
+  if (!ctx || !d_comp_off || !d_out_off || !d_out_len || !d_status || !d_err_off) return FB200_ERR_ARG;
+  int rc = inflate_launch(ctx, d_comp, d_comp_off, nstreams, d_out, d_out_off, d_out_len, d_status, d_err_off,
+                          d_consumed, ~0ull, InflateHooks{});
+  if (rc != FB200_OK) return rc;
+  return inflate_finish(ctx);
+}
+
+// Host-buffer inflate.  One launch for the whole batch; the compressed input is copied in chunks on a second
+// stream that advances the arrival watermark the kernel waits on, and the kernel publishes finished output
+// groups through host-visible flags, so the D2H copy of group g runs while later groups are still being
+// decoded.  If any stream had to be re-decoded by the exact kernel, the output is copied once more at the end.
 extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const uint64_t *comp_off, uint64_t nstreams,
                                    uint8_t *out, const uint64_t *out_off, uint64_t *out_len, int32_t *status,
                                    int64_t *err_off, uint64_t *consumed)
@@ -596,86 +661,120 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
   if (!ctx || !comp_off || !out_off || !out_len || !status || !err_off) return FB200_ERR_ARG;
   for (uint64_t i = 0; i < nstreams; i++)
     if (comp_off[i + 1] < comp_off[i] || out_off[i + 1] < out_off[i]) { ctx->err = "offsets not monotone"; return FB200_ERR_ARG; }
-  const uint64_t nc = nstreams ? comp_off[nstreams] - comp_off[0] : 0;
-  const uint64_t no = nstreams ? out_off[nstreams] - out_off[0] : 0;
+  const uint64_t c0 = nstreams ? comp_off[0] : 0, o0 = nstreams ? out_off[0] : 0;
+  const uint64_t nc = nstreams ? comp_off[nstreams] - c0 : 0;
+  const uint64_t no = nstreams ? out_off[nstreams] - o0 : 0;
   if ((!comp && nc) || (!out && no)) return FB200_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   ctx->stats = fb200_stats{};
   if (nstreams == 0) return FB200_OK;
+  if (nstreams > 0xfffffff0ull) return FB200_ERR_ARG;
   cudaStream_t st = ctx->stream;
-  // chunks of whole streams, two-slot pipeline as in deflate_host_common
-  struct Chunk { uint64_t a, b; };
-  std::vector<Chunk> chunks;
-  uint64_t max_c = 0, max_o = 0, max_cnt = 0;
-  for (uint64_t a = 0; a < nstreams;) {
-    uint64_t b = a;
-    while (b < nstreams && (b == a || (out_off[b] - out_off[a] < ctx->chunk_bytes && comp_off[b] - comp_off[a] < ctx->chunk_bytes)))
-      b++;
-    chunks.push_back({a, b});
-    if (comp_off[b] - comp_off[a] > max_c) max_c = comp_off[b] - comp_off[a];
-    if (out_off[b] - out_off[a] > max_o) max_o = out_off[b] - out_off[a];
-    if (b - a > max_cnt) max_cnt = b - a;
-    a = b;
-  }
-  for (int i = 0; i < 2; i++) {
-    CK(ctx->p_in[i].ensure(max_c + 16));
-    CK(ctx->p_out[i].ensure(max_o + 16));
-    CK(ctx->p_off_in[i].ensure((max_cnt + 1) * 8));
-    CK(ctx->p_off_out[i].ensure((max_cnt + 1) * 8));
-    CK(ctx->p_len[i].ensure((max_cnt + 1) * 8));
-    CK(ctx->p_status[i].ensure((max_cnt + 1) * 4));
-    CK(ctx->p_eoff[i].ensure((max_cnt + 1) * 8));
-    CK(ctx->p_cons[i].ensure((max_cnt + 1) * 8));
-  }
+  const bool overlap = ctx->inflate_mode != 2;
+  // output groups: ~chunk_bytes of output capacity each, at most kMaxChunks of them
+  uint64_t gs = no ? (uint64_t)((double)ctx->chunk_bytes / ((double)no / (double)nstreams)) : nstreams;
+  if (gs == 0) gs = 1;
+  if ((nstreams + gs - 1) / gs > (uint64_t)fb200_ctx::kMaxChunks) gs = (nstreams + fb200_ctx::kMaxChunks - 1) / fb200_ctx::kMaxChunks;
+  const uint64_t ngroups = (nstreams + gs - 1) / gs;
+  CK(ctx->p_in[0].ensure(nc + 256));
+  CK(ctx->p_out[0].ensure(no + 16));
+  CK(ctx->p_off_in[0].ensure((nstreams + 1) * 8));
+  CK(ctx->p_off_out[0].ensure((nstreams + 1) * 8));
+  CK(ctx->p_len[0].ensure((nstreams + 1) * 8));
+  CK(ctx->p_status[0].ensure((nstreams + 1) * 4));
+  CK(ctx->p_eoff[0].ensure((nstreams + 1) * 8));
+  CK(ctx->p_cons[0].ensure((nstreams + 1) * 8));
   CK(ctx->all_off.ensure((nstreams + 1) * 8));
   CK(ctx->all_off2.ensure((nstreams + 1) * 8));
+  CK(ctx->group_done.ensure(ngroups * 4));
+  uint8_t *d_comp = ctx->p_in[0].as<uint8_t>();
+  uint8_t *d_out = ctx->p_out[0].as<uint8_t>();
+  CK(cudaMemsetAsync(ctx->d_wm, 0, 8, st));
+  CK(cudaMemsetAsync(ctx->group_done.p, 0, ngroups * 4, st));
+  for (uint64_t g = 0; g < ngroups; g++) ctx->h_flags[g] = 0;
+  CK(cudaEventRecord(ctx->e_comp[0], st));
+  CK(cudaStreamWaitEvent(ctx->s_in, ctx->e_comp[0], 0));
   CK(cudaMemcpyAsync(ctx->all_off.p, comp_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
   CK(cudaMemcpyAsync(ctx->all_off2.p, out_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-  auto issue_h2d = [&](size_t c) -> int {
-    const Chunk &ch = chunks[c];
-    const int slot = (int)(c & 1);
-    const uint64_t cb = comp_off[ch.b] - comp_off[ch.a];
-    if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ctx->e_comp[slot], 0));
-    if (cb) CK(cudaMemcpyAsync(ctx->p_in[slot].p, comp + comp_off[ch.a], cb, cudaMemcpyHostToDevice, ctx->s_in));
-    launch_affine_u64(ctx->p_off_in[slot].as<uint64_t>(), ctx->all_off.as<uint64_t>() + ch.a, ch.b - ch.a + 1,
-                      0ull - comp_off[ch.a], ctx->s_in);
-    launch_affine_u64(ctx->p_off_out[slot].as<uint64_t>(), ctx->all_off2.as<uint64_t>() + ch.a, ch.b - ch.a + 1,
-                      0ull - out_off[ch.a], ctx->s_in);
-    CK(cudaEventRecord(ctx->e_in[slot], ctx->s_in));
-    return FB200_OK;
-  };
-  int rc = issue_h2d(0);
-  if (rc != FB200_OK) return rc;
-  uint64_t launches = 0, fallbacks = 0;
-  for (size_t c = 0; c < chunks.size(); c++) {
-    const Chunk &ch = chunks[c];
-    const int slot = (int)(c & 1);
-    const uint64_t cnt = ch.b - ch.a;
-    if (c + 1 < chunks.size() && (rc = issue_h2d(c + 1)) != FB200_OK) return rc;
-    CK(cudaStreamWaitEvent(st, ctx->e_in[slot], 0));
-    if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->e_out[slot], 0));
-    rc = fb200_inflate_batch_dev(ctx, ctx->p_in[slot].as<uint8_t>(), ctx->p_off_in[slot].as<uint64_t>(), cnt,
-                                 ctx->p_out[slot].as<uint8_t>(), ctx->p_off_out[slot].as<uint64_t>(),
-                                 ctx->p_len[slot].as<uint64_t>(), ctx->p_status[slot].as<int32_t>(),
-                                 ctx->p_eoff[slot].as<int64_t>(), ctx->p_cons[slot].as<uint64_t>());
-    if (rc != FB200_OK) return rc;
-    launches += ctx->stats.kernel_launches + 2;
-    fallbacks += ctx->stats.inflate_fallbacks;
-    CK(cudaEventRecord(ctx->e_comp[slot], st));
-    CK(cudaStreamWaitEvent(ctx->s_out, ctx->e_comp[slot], 0));
-    const uint64_t ob = out_off[ch.b] - out_off[ch.a];
-    if (ob) CK(cudaMemcpyAsync(out + out_off[ch.a], ctx->p_out[slot].p, ob, cudaMemcpyDeviceToHost, ctx->s_out));
-    CK(cudaMemcpyAsync(out_len + ch.a, ctx->p_len[slot].p, cnt * 8, cudaMemcpyDeviceToHost, ctx->s_out));
-    CK(cudaMemcpyAsync(status + ch.a, ctx->p_status[slot].p, cnt * 4, cudaMemcpyDeviceToHost, ctx->s_out));
-    CK(cudaMemcpyAsync(err_off + ch.a, ctx->p_eoff[slot].p, cnt * 8, cudaMemcpyDeviceToHost, ctx->s_out));
-    if (consumed) CK(cudaMemcpyAsync(consumed + ch.a, ctx->p_cons[slot].p, cnt * 8, cudaMemcpyDeviceToHost, ctx->s_out));
-    CK(cudaEventRecord(ctx->e_out[slot], ctx->s_out));
+  CK(cudaEventRecord(ctx->e_in[0], ctx->s_in));
+  CK(cudaStreamWaitEvent(st, ctx->e_in[0], 0));
+  launch_affine_u64(ctx->p_off_in[0].as<uint64_t>(), ctx->all_off.as<uint64_t>(), nstreams + 1, 0ull - c0, st);
+  launch_affine_u64(ctx->p_off_out[0].as<uint64_t>(), ctx->all_off2.as<uint64_t>(), nstreams + 1, 0ull - o0, st);
+  static const bool trace = getenv("FB200_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  double t_first = 0, t_last = 0, t_fed = 0;
+  InflateHooks hk;
+  if (overlap) {
+    hk.avail = ctx->d_wm + 1;
+    hk.group_done = ctx->group_done.as<uint32_t>();
+    hk.group_flag = ctx->h_flags;
+    hk.group_streams = (uint32_t)gs;
+  } else {
+    // everything resident before the kernels start
+    if (nc) CK(cudaMemcpyAsync(d_comp, comp + c0, nc, cudaMemcpyHostToDevice, st));
   }
+  int rc = inflate_launch(ctx, d_comp, ctx->p_off_in[0].as<uint64_t>(), nstreams, d_out, ctx->p_off_out[0].as<uint64_t>(),
+                          ctx->p_len[0].as<uint64_t>(), ctx->p_status[0].as<int32_t>(), ctx->p_eoff[0].as<int64_t>(),
+                          ctx->p_cons[0].as<uint64_t>(), no, hk);
+  if (rc != FB200_OK) return rc;
+  if (overlap) {
+    // feed the kernel: input chunks (boundaries rounded up to 128 bytes) + watermark
+    uint64_t step = ctx->chunk_bytes;
+    if (nc / step + 2 > (uint64_t)fb200_ctx::kMaxChunks) step = nc / (fb200_ctx::kMaxChunks - 2) + 1;
+    uint64_t done = 0, next_cut = step;
+    size_t c = 0;
+    for (uint64_t i = 0; i < nstreams; i++) {
+      const uint64_t endb = comp_off[i + 1] - c0;
+      if (endb >= next_cut || i + 1 == nstreams) {
+        uint64_t upto = i + 1 == nstreams ? nc : ((endb + 127) & ~127ull);
+        if (upto > nc) upto = nc;
+        if (upto > done) {
+          CK(cudaMemcpyAsync(d_comp + done, comp + c0 + done, upto - done, cudaMemcpyHostToDevice, ctx->s_in));
+          done = upto;
+        }
+        ctx->wm_vals[c] = (uint32_t)(i + 1);
+        CK(cudaMemcpyAsync(ctx->d_wm + 1, &ctx->wm_vals[c], 4, cudaMemcpyHostToDevice, ctx->s_in));
+        c++;
+        next_cut = endb + step;
+      }
+    }
+    t_fed = now();
+    // drain: copy every output group back as soon as the device reports it finished
+    for (uint64_t g = 0; g < ngroups; g++) {
+      unsigned spins = 0;
+      while (ctx->h_flags[g] == 0) {
+        if ((++spins & 0x3ff) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break; // finished, or failed
+      }
+      if (ctx->h_flags[g] == 0) break; // the stream ended without the flag: error path below reports it
+      const uint64_t a = g * gs, b = a + gs < nstreams ? a + gs : nstreams;
+      const uint64_t ob = out_off[b] - out_off[a];
+      if (ob) CK(cudaMemcpyAsync(out + out_off[a], d_out + (out_off[a] - o0), ob, cudaMemcpyDeviceToHost, ctx->s_out));
+      if (g == 0) t_first = now();
+      t_last = now();
+    }
+  }
+  rc = inflate_finish(ctx);
+  if (rc != FB200_OK) return rc;
+  const double t_kdone = now();
+  if (!overlap || ctx->stats.inflate_fallbacks) { // (re-)copy the whole output: exact-kernel results came last
+    CK(cudaStreamSynchronize(ctx->s_out));
+    if (no) CK(cudaMemcpyAsync(out + o0, d_out, no, cudaMemcpyDeviceToHost, st));
+  } else {
+    for (uint64_t g = 0; g < ngroups; g++)
+      if (ctx->h_flags[g] == 0) { ctx->err = "internal error: output group never completed"; return FB200_ERR_CUDA; }
+  }
+  CK(cudaMemcpyAsync(out_len, ctx->p_len[0].p, nstreams * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(status, ctx->p_status[0].p, nstreams * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(err_off, ctx->p_eoff[0].p, nstreams * 8, cudaMemcpyDeviceToHost, st));
+  if (consumed) CK(cudaMemcpyAsync(consumed, ctx->p_cons[0].p, nstreams * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   CK(cudaStreamSynchronize(ctx->s_in));
   CK(cudaStreamSynchronize(ctx->s_out));
-  CK(cudaStreamSynchronize(st));
-  ctx->stats.kernel_launches = launches;
-  ctx->stats.inflate_fallbacks = fallbacks;
+  ctx->stats.kernel_launches += 2;
+  if (trace)
+    fprintf(stderr, "[fb200] inflate host: groups=%llu fed=%.2f first_flag=%.2f last_flag=%.2f kernels_done=%.2f end=%.2f ms\n",
+            (unsigned long long)ngroups, t_fed - t0, t_first - t0, t_last - t0, t_kdone - t0, now() - t0);
   return FB200_OK;
 }
 

@@ -342,4 +342,16 @@ void launch_pack(const DeflateJob &j, cudaStream_t st)
   }
 }
 
+// CUDA loads kernels lazily, and loading one while another kernel spins on a host-fed watermark can
+// deadlock: every kernel of this file is loaded when the context is created.
+void preload_encode_kernels()
+{
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_histogram);
+  cudaFuncGetAttributes(&a, k_build_codes);
+  cudaFuncGetAttributes(&a, k_layout);
+  cudaFuncGetAttributes(&a, k_pack);
+  cudaFuncGetAttributes(&a, k_trailer);
+}
+
 } // namespace fb

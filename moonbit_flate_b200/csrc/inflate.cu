@@ -366,6 +366,11 @@ __global__ void __launch_bounds__(kFastWarps * 32, 10) k_inflate_fast(InflateJob
     if (lane == 0) st32 = atomicAdd(&j.counters[0], 1u);
     st32 = __shfl_sync(kFull, st32, 0);
     if (st32 >= j.nstreams) break;
+    if (j.avail) { // host-buffer call: wait until the H2D stream has delivered this stream's bytes
+      if (lane == 0)
+        while (*(volatile const uint32_t *)j.avail <= st32) __nanosleep(500);
+      __syncwarp();
+    }
 
     const uint8_t *in = j.comp + j.comp_off[st32];
     const uint64_t in_len = j.comp_off[st32 + 1] - j.comp_off[st32];
@@ -566,6 +571,19 @@ __global__ void __launch_bounds__(kFastWarps * 32, 10) k_inflate_fast(InflateJob
       }
     }
     __syncwarp();
+    if (j.group_done) { // host-buffer call: publish finished output groups so their D2H copy can start
+      __threadfence();
+      if (lane == 0) {
+        const uint32_t g = st32 / j.group_streams;
+        const uint32_t first = g * j.group_streams;
+        const uint32_t cnt = (uint32_t)(j.nstreams - first < j.group_streams ? j.nstreams - first : j.group_streams);
+        if (atomicAdd(&j.group_done[g], 1u) + 1u == cnt) {
+          __threadfence_system();
+          j.group_flag[g] = 1u;
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -850,6 +868,15 @@ void launch_inflate(const InflateJob &j, int num_sms, bool fast_v1, cudaStream_t
   k_inflate_fast<<<g, kFastWarps * 32, 0, st>>>(j);
   // exact re-decode of whatever the fast path put on the fallback list (usually nothing)
   k_inflate<<<(unsigned)num_sms * 2, kInflateWarps * 32, 0, st>>>(j);
+}
+
+// CUDA loads kernels lazily, and loading one while another kernel spins on a host-fed watermark can
+// deadlock: every kernel of this file is loaded when the context is created.
+void preload_inflate_kernels()
+{
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_inflate_fast);
+  cudaFuncGetAttributes(&a, k_inflate);
 }
 
 } // namespace fb

@@ -566,6 +566,16 @@ __global__ void k_order_scatter(InflateJob j, uint32_t *hist, uint32_t *order)
   if (i < j.nstreams) order[atomicAdd(&hist[order_bucket(j.comp_off[i + 1] - j.comp_off[i])], 1u)] = (uint32_t)i;
 }
 
+// decode order only (used by the other fast paths as well)
+void launch_stream_order(const InflateJob &j, uint32_t *order_hist, cudaStream_t st)
+{
+  const unsigned gs = (unsigned)((j.nstreams + 255) / 256);
+  cudaMemsetAsync(order_hist, 0, kOrderBuckets * sizeof(uint32_t), st);
+  k_order_count<<<gs, 256, 0, st>>>(j, order_hist);
+  k_order_scan<<<1, kOrderBuckets, 0, st>>>(order_hist);
+  k_order_scatter<<<gs, 256, 0, st>>>(j, order_hist, const_cast<uint32_t *>(j.order));
+}
+
 template <int S>
 static void launch_decode(const InflateJob &j, int num_sms, cudaStream_t st)
 {
@@ -589,17 +599,28 @@ void launch_inflate2(const InflateJob &j, int num_sms, uint32_t *order_hist, cud
     spw = e ? atoi(e) : 8;
     if (spw != 8 && spw != 16 && spw != 32) spw = 8;
   }
-  const unsigned gs = (unsigned)((j.nstreams + 255) / 256);
-  cudaMemsetAsync(order_hist, 0, kOrderBuckets * sizeof(uint32_t), st);
-  k_order_count<<<gs, 256, 0, st>>>(j, order_hist);
-  k_order_scan<<<1, kOrderBuckets, 0, st>>>(order_hist);
-  k_order_scatter<<<gs, 256, 0, st>>>(j, order_hist, const_cast<uint32_t *>(j.order));
+  launch_stream_order(j, order_hist, st);
   if (spw == 8) launch_decode<8>(j, num_sms, st);
   else if (spw == 16) launch_decode<16>(j, num_sms, st);
   else launch_decode<32>(j, num_sms, st);
   const uint64_t wantc = (j.nstreams + 3) / 4;
   const uint64_t maxc = (uint64_t)num_sms * 16;
   k_inflate_copy<<<(unsigned)(wantc < maxc ? wantc : maxc), 128, 0, st>>>(j);
+}
+
+// CUDA loads kernels lazily, and loading one while another kernel spins on a host-fed watermark can
+// deadlock: every kernel of this file is loaded when the context is created.
+void preload_inflate2_kernels()
+{
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_inflate_decode<8>);
+  cudaFuncGetAttributes(&a, k_inflate_decode<16>);
+  cudaFuncGetAttributes(&a, k_inflate_decode<32>);
+  cudaFuncGetAttributes(&a, k_inflate_copy);
+  cudaFuncGetAttributes(&a, k_rec_off);
+  cudaFuncGetAttributes(&a, k_order_count);
+  cudaFuncGetAttributes(&a, k_order_scan);
+  cudaFuncGetAttributes(&a, k_order_scatter);
 }
 
 } // namespace fb

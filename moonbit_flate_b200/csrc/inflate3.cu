@@ -1,0 +1,598 @@
+// inflate3.cu -- K6 fast path: one warp per stream, the 32 lanes decode ONE block in parallel.
+//
+// Huffman decoding is a serial chain (the position of a symbol is known only once the previous one has been
+// decoded), ~100 dependent cycles per symbol on a GPU thread; a 64 KiB segment of 25..65 k symbols costs
+// milliseconds per stream however many streams run side by side.  The chain is broken speculatively:
+//
+//   * the bits of a block are cut into 32 equal ranges; lane i starts decoding at the first bit of range i
+//     -- almost certainly not a symbol boundary -- and runs to the end of its range.  Huffman streams
+//     self-synchronise: after a few (wrong) symbols the lane falls onto true boundaries, so the position
+//     p_i where it leaves its range is usually the true one;
+//   * lane i then takes p_{i-1} as its start and decodes its range again, counting output bytes and
+//     back-references; this is repeated until no start moves (lane 0 starts at the true first bit, so
+//     lane k is final after round k at the latest: usually two rounds, always <= 33);
+//   * the chain is valid up to the first lane that met the end-of-block code; an exclusive scan of the
+//     per-lane counts gives every lane its output position, and a last pass writes the literals to
+//     their final place and records the back-references {dst, len, dist};
+//   * the recorded copies are replayed in order by the warp (DictDecoder::write_copy semantics,
+//     dict-decoder.mbt:114-185): records whose source lies before the first unresolved destination are
+//     independent and are copied one per lane, long ones by the whole warp.
+//
+// Block headers, stored blocks and the tables (inflate.mbt:345-548) are handled warp-uniformly as in the
+// exact kernel's fast sibling.  Anything unusual -- a header the reference rejects, an invalid symbol on
+// the true path, a distance beyond the output, a slot that is too small, truncated input -- puts the
+// stream on the fallback list: k_inflate (inflate.cu) then re-decodes it with the reference's exact error
+// behaviour.  A stream that completes here consumed only real bits and every block ended in its EOB, so
+// the reference decodes it to the same bytes with status EOF.
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/flate_b200.h"
+
+#include <cstdlib>
+
+namespace fb {
+namespace par {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kLB = 10;
+constexpr int kDB = 8;
+constexpr int kWarps = 4;
+constexpr uint32_t kLitLim = 256u << 4; // table entry = (symbol << 4) | code length
+constexpr uint32_t P_OK = 0, P_EOB = 1, P_BAD = 2;
+constexpr uint32_t kMinRange = 256;     // bits per lane at least
+constexpr int kLaneCopyMax = 24;
+
+struct Tab {
+  uint16_t first[16], count[16], offs[16];
+};
+
+struct Smem { // one warp
+  uint16_t lit[1 << kLB];
+  uint16_t dist[1 << kDB];
+  uint16_t cl[128];
+  uint16_t lsorted[288];
+  uint16_t dsorted[32];
+  Tab tl, td;
+  uint8_t lens[320];
+  uint8_t cl_lens[32];
+};
+
+__constant__ uint32_t c3_len_tab[32] = {
+    3,           4,           5,           6,           7,           8,           9,           10,
+    11 | 1 << 16, 13 | 1 << 16, 15 | 1 << 16, 17 | 1 << 16, 19 | 2 << 16, 23 | 2 << 16, 27 | 2 << 16, 31 | 2 << 16,
+    35 | 3 << 16, 43 | 3 << 16, 51 | 3 << 16, 59 | 3 << 16, 67 | 4 << 16, 83 | 4 << 16, 99 | 4 << 16, 115 | 4 << 16,
+    131 | 5 << 16, 163 | 5 << 16, 195 | 5 << 16, 227 | 5 << 16, 258, 0, 0, 0};
+__constant__ uint32_t c3_dist_tab[32] = {
+    1,            2,            3,             4,             5 | 1 << 16,    7 | 1 << 16,    9 | 2 << 16,     13 | 2 << 16,
+    17 | 3 << 16, 25 | 3 << 16, 33 | 4 << 16,  49 | 4 << 16,  65 | 5 << 16,   97 | 5 << 16,   129 | 6 << 16,   193 | 6 << 16,
+    257 | 7 << 16, 385 | 7 << 16, 513 | 8 << 16, 769 | 8 << 16, 1025 | 9 << 16, 1537 | 9 << 16, 2049 | 10 << 16, 3073 | 10 << 16,
+    4097 | 11 << 16, 6145 | 11 << 16, 8193 | 12 << 16, 12289 | 12 << 16, 16385 | 13 << 16, 24577 | 13 << 16, 0, 0};
+__constant__ uint8_t c3_code_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// HuffmanDecoder::initialize (inflate.mbt:100-223), warp-cooperative: canonical description only.
+// false = the reference rejects the code (or it is empty): exact path.
+__device__ bool warp_canon(const uint8_t *lens, int nsym, uint16_t *sorted, Tab *tab, int *mn_out, int *mx_out)
+{
+  const int lane = threadIdx.x & 31;
+  int c = 0;
+  if (lane >= 1 && lane <= 15)
+    for (int i = 0; i < nsym; i++) c += (lens[i] == lane);
+  const unsigned nz = __ballot_sync(kFull, c != 0);
+  if (nz == 0) return false;
+  const int mn = __ffs(nz) - 1, mx = 31 - __clz(nz);
+  int code = 0, off = 0, code_at_max = 0, my_first = 0, my_off = 0;
+  for (int L = 1; L <= 15; L++) {
+    const int cL = __shfl_sync(kFull, c, L);
+    code <<= 1;
+    if (lane == L) { my_first = code; my_off = off; }
+    code += cL;
+    off += cL;
+    if (L == mx) code_at_max = code;
+  }
+  if (code_at_max != (1 << mx) && !(code_at_max == 1 && mx == 1)) return false; // :161
+  if (lane < 16) {
+    tab->first[lane] = (uint16_t)my_first;
+    tab->count[lane] = (uint16_t)c;
+    tab->offs[lane] = (uint16_t)my_off;
+  }
+  if (c) {
+    int k = my_off;
+    for (int i = 0; i < nsym; i++)
+      if (lens[i] == lane) sorted[k++] = (uint16_t)i;
+  }
+  *mn_out = mn;
+  *mx_out = mx;
+  __syncwarp();
+  return true;
+}
+
+__device__ void warp_fill_lut(uint16_t *lut, int lut_bits, const uint16_t *sorted, const Tab *tab, int mn, int mx)
+{
+  const int lane = threadIdx.x & 31;
+  for (int idx = lane; idx < (1 << lut_bits); idx += 32) {
+    const unsigned r = __brev((unsigned)idx);
+    uint32_t e = 0;
+    for (int L = mn; L <= lut_bits && L <= mx; L++) {
+      const unsigned d = (r >> (32 - L)) - tab->first[L];
+      if (d < tab->count[L]) {
+        e = (uint32_t)((sorted[tab->offs[L] + d] << 4) | L);
+        break;
+      }
+    }
+    lut[idx] = (uint16_t)e;
+  }
+  __syncwarp();
+}
+
+// code longer than the direct table: (sym << 4) | len, 0 if none matches
+__device__ __forceinline__ uint32_t canon_long(uint32_t bits, int from, const Tab *tab, const uint16_t *sorted)
+{
+  const unsigned r = __brev(bits);
+  for (int L = from; L <= 15; L++) {
+    const unsigned d = (r >> (32 - L)) - tab->first[L];
+    if (d < tab->count[L]) return ((uint32_t)sorted[tab->offs[L] + d] << 4) | (uint32_t)L;
+  }
+  return 0;
+}
+
+// Warp-uniform bit reader for the headers: every lane holds the same state and issues the same loads.
+struct UBits {
+  const uint32_t *w;
+  const uint8_t *end;
+  uint64_t bb;
+  int nb;
+  __device__ __forceinline__ void init(const uint8_t *in, uint64_t len)
+  {
+    end = in + len;
+    bb = 0; nb = 0;
+    const uint8_t *p = in;
+    while (reinterpret_cast<uintptr_t>(p) & 3) {
+      if (p < end) bb |= (uint64_t)__ldg(p) << nb;
+      nb += 8;
+      p++;
+    }
+    w = reinterpret_cast<const uint32_t *>(p);
+  }
+  __device__ __forceinline__ void refill()
+  {
+    if (nb < 32) {
+      uint32_t v = 0;
+      if (reinterpret_cast<const uint8_t *>(w) < end) v = __ldg(w);
+      bb |= (uint64_t)v << nb;
+      nb += 32;
+      w++;
+    }
+  }
+  __device__ __forceinline__ uint32_t peek() const { return (uint32_t)bb; }
+  __device__ __forceinline__ void drop(int n) { bb >>= n; nb -= n; }
+  __device__ __forceinline__ uint32_t take(int n)
+  {
+    const uint32_t v = (uint32_t)bb & ((1u << n) - 1u);
+    drop(n);
+    return v;
+  }
+  __device__ __forceinline__ int64_t consumed_bits(const uint8_t *in) const
+  {
+    return (int64_t)(reinterpret_cast<const uint8_t *>(w) - in) * 8 - nb;
+  }
+};
+
+// Per-lane bit reader: a 64-bit window (hi:lo) with bit offset bo < 32 exposes >= 33 valid bits, enough for a
+// code with its extra bits; the word after the window is requested one step ahead.  Positions are 32-bit
+// word indices from the aligned word at or below the first byte (the base pointer is warp-uniform).
+struct LBits {
+  const uint32_t *base;
+  uint32_t nwords; // words that may be read
+  uint32_t wi;     // index of `lo`
+  uint32_t lo, hi, nx;
+  int bo;
+  __device__ __forceinline__ uint32_t ld(uint32_t i) const { return i < nwords ? __ldg(base + i) : 0u; }
+  // abit = bit position counted from `base`
+  __device__ __forceinline__ void init(const uint32_t *b, uint32_t nw, uint32_t abit)
+  {
+    base = b;
+    nwords = nw;
+    wi = abit >> 5;
+    bo = (int)(abit & 31u);
+    lo = ld(wi); hi = ld(wi + 1); nx = ld(wi + 2);
+  }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bo); }
+  __device__ __forceinline__ void drop(int n)
+  {
+    bo += n;
+    if (bo >= 32) {
+      lo = hi; hi = nx;
+      wi++;
+      nx = ld(wi + 2);
+      bo -= 32;
+    }
+  }
+  __device__ __forceinline__ uint32_t abit() const { return (wi << 5) + (uint32_t)bo; }
+};
+
+// Every lane with `run` decodes from bit `start` until it reaches bit `e` (or EOB, or something invalid);
+// bit positions are relative to `in`.  WRITE: literals go to out[obase + ...], back-references to rec[...]
+// with absolute destinations.
+template <bool WRITE>
+__device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_len_tab, const uint32_t *s_dist_tab,
+                                              const uint8_t *in, int64_t cur_len, uint32_t bend, bool run,
+                                              uint32_t start, uint32_t e, uint32_t &p_out, uint32_t &flag_out,
+                                              uint32_t &n_out, uint32_t &n_rec, uint8_t *out, uint32_t obase,
+                                              uint2 *rec)
+{
+  const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
+  const uint32_t *wbase = reinterpret_cast<const uint32_t *>(in - lead);
+  const uint32_t lead_bits = lead * 8u;
+  LBits lb;
+  lb.init(wbase, (uint32_t)((cur_len + lead + 3) >> 2), (run ? start : 0u) + lead_bits);
+  const uint32_t e_abs = e + lead_bits, bend_abs = bend + lead_bits;
+  uint32_t flag = P_OK, cnt_out = 0, cnt_rec = 0;
+  bool act = run && start < e;
+  while (__any_sync(kFull, act)) {
+    const uint32_t bits = lb.peek();
+    uint32_t e0 = act ? sm.lit[bits & ((1u << kLB) - 1u)] : 1u;
+    if (__any_sync(kFull, e0 == 0)) {
+      if (e0 == 0) e0 = canon_long(bits, kLB + 1, &sm.tl, sm.lsorted);
+    }
+    const uint32_t cl = e0 & 15u, sym = e0 >> 4;
+    const bool is_len = act && sym > 256u && sym < (uint32_t)kNumLit;
+    uint32_t length = 0;
+    if (act) {
+      if (e0 == 0 || sym >= (uint32_t)kNumLit) { flag = P_BAD; act = false; }
+      else {
+        const uint32_t lt = is_len ? s_len_tab[sym - 257u] : 0u;
+        const uint32_t xb = lt >> 16;
+        length = (lt & 0xffffu) + ((bits >> cl) & ((1u << xb) - 1u));
+        lb.drop((int)(cl + xb));
+        if (sym < 256u) {
+          if (WRITE) out[obase + cnt_out] = (uint8_t)sym;
+          cnt_out++;
+        } else if (sym == 256u) { flag = P_EOB; act = false; }
+      }
+    }
+    if (__any_sync(kFull, is_len && act)) {
+      if (is_len && act) {
+        const uint32_t dbits = lb.peek();
+        uint32_t d = sm.dist[dbits & ((1u << kDB) - 1u)];
+        if (d == 0) d = canon_long(dbits, kDB + 1, &sm.td, sm.dsorted);
+        if (d == 0 || (d >> 4) >= (uint32_t)kNumDist) { flag = P_BAD; act = false; }
+        else {
+          const uint32_t dl = d & 15u;
+          const uint32_t dt = s_dist_tab[d >> 4];
+          const uint32_t dxb = dt >> 16;
+          lb.drop((int)(dl + dxb));
+          if (WRITE) {
+            const uint32_t dist = (dt & 0xffffu) + ((dbits >> dl) & ((1u << dxb) - 1u));
+            const uint32_t at = obase + cnt_out;
+            if (dist > at) { flag = P_BAD; act = false; } // dist > hist_size (inflate.mbt:677)
+            else rec[cnt_rec] = make_uint2(at, length | ((dist - 1u) << 16));
+          }
+          cnt_out += length;
+          cnt_rec++;
+        }
+      }
+    }
+    if (act) {
+      const uint32_t ab = lb.abit();
+      if (ab > bend_abs) { flag = P_BAD; act = false; } // ran past the end of the input
+      else if (ab >= e_abs) act = false;
+    }
+  }
+  p_out = (run && start < e) ? lb.abit() - lead_bits : start;
+  flag_out = flag;
+  n_out = cnt_out;
+  n_rec = cnt_rec;
+}
+
+// Replays records [0, nrec) of one stream in order.
+__device__ void replay_records(uint8_t *out, const uint2 *rec, uint32_t nrec, int lane)
+{
+  for (uint32_t g = 0; g < nrec; g += 32) {
+    const uint32_t r = g + (uint32_t)lane;
+    uint32_t dst = 0, len = 0, dist = 1;
+    if (r < nrec) {
+      const uint2 v = rec[r];
+      dst = v.x; len = v.y & 0xffffu; dist = (v.y >> 16) + 1u;
+    }
+    const bool big = len > (uint32_t)kLaneCopyMax;
+    // source interval: [dst - dist, dst - dist + min(len, dist))
+    const uint32_t src_end = dst - dist + (len < dist ? len : dist);
+    unsigned pending = __ballot_sync(kFull, r < nrec);
+    while (pending) {
+      const int p = __ffs(pending) - 1;
+      const uint32_t dstp = __shfl_sync(kFull, dst, p);
+      const bool bigp = __shfl_sync(kFull, (int)big, p) != 0;
+      if (bigp) { // the whole warp copies record p
+        const uint32_t lenp = __shfl_sync(kFull, len, p);
+        const uint32_t dd = __shfl_sync(kFull, dist, p);
+        uint8_t *dp = out + dstp;
+        const uint8_t *sp = dp - dd;
+        if (dd >= 32u) {
+          // pieces of at most dd bytes never read what they write; 32 bytes per step inside a piece
+          for (uint32_t b0 = 0; b0 < lenp; b0 += dd) {
+            const uint32_t b1 = b0 + dd < lenp ? b0 + dd : lenp;
+            for (uint32_t i = b0 + lane; i < b1; i += 32) dp[i] = __ldcg(sp + i);
+            __syncwarp();
+          }
+        } else { // overlapping: the pattern of dd bytes repeats (dict-decoder.mbt:136-149)
+          for (uint32_t i = lane; i < lenp; i += 32) dp[i] = __ldcg(sp + (i % dd));
+        }
+        pending &= ~(1u << p);
+        __syncwarp();
+        continue;
+      }
+      // parallel round: every pending small record whose source lies before the first unresolved destination,
+      // up to the first pending big record (records after it may depend on it)
+      const bool mine = ((pending >> lane) & 1u) && !big && (lane == p || src_end <= dstp);
+      const unsigned bigm = __ballot_sync(kFull, big) & pending;
+      const unsigned ready = __ballot_sync(kFull, mine) & (bigm ? ((1u << (__ffs(bigm) - 1)) - 1u) : kFull);
+      if ((ready >> lane) & 1u) {
+        uint8_t *dp = out + dst;
+        const uint8_t *sp = dp - dist;
+        uint8_t v[kLaneCopyMax];
+        if (dist >= len) {
+#pragma unroll
+          for (int k = 0; k < kLaneCopyMax; k++)
+            if ((uint32_t)k < len) v[k] = __ldcg(sp + k);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kLaneCopyMax; k++)
+            if ((uint32_t)k < len) v[k] = __ldcg(sp + ((uint32_t)k % dist));
+        }
+#pragma unroll
+        for (int k = 0; k < kLaneCopyMax; k++)
+          if ((uint32_t)k < len) dp[k] = v[k];
+      }
+      pending &= ~ready;
+      __syncwarp();
+    }
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
+{
+  __shared__ Smem smem_all[kWarps];
+  __shared__ uint32_t s_len_tab[32], s_dist_tab[32];
+  Smem &sm = smem_all[threadIdx.x >> 5];
+  if (threadIdx.x < 32) {
+    s_len_tab[threadIdx.x] = c3_len_tab[threadIdx.x];
+    s_dist_tab[threadIdx.x] = c3_dist_tab[threadIdx.x];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+
+  for (;;) {
+    uint32_t st32 = 0;
+    if (lane == 0) st32 = atomicAdd(&j.counters[0], 1u);
+    st32 = __shfl_sync(kFull, st32, 0);
+    if (st32 >= j.nstreams) break;
+    if (j.order) st32 = j.order[st32]; // device-resident calls: longest streams first
+    if (j.avail) { // host-buffer call: wait until the H2D stream has delivered this stream's bytes
+      if (lane == 0)
+        while (*(volatile const uint32_t *)j.avail <= st32) __nanosleep(500);
+      __syncwarp();
+    }
+    const uint8_t *in0 = j.comp + j.comp_off[st32];
+    const uint8_t *in = in0;
+    const uint64_t in_len = j.comp_off[st32 + 1] - j.comp_off[st32];
+    uint8_t *out = j.out + j.out_off[st32];
+    const uint64_t cap64 = j.out_off[st32 + 1] - j.out_off[st32];
+    const uint32_t cap = cap64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)cap64;
+    uint2 *rec = j.records + j.rec_off[st32];
+    const uint32_t rec_cap = (uint32_t)(j.rec_off[st32 + 1] - j.rec_off[st32]);
+    uint32_t nrec = 0, opos = 0;
+    int64_t cur_len = (int64_t)in_len; // bytes from `in` (re-based after every block) to the end
+    UBits ub;
+    ub.init(in, in_len);
+    bool bail = in_len > 0x0fffffffull; // keep bit positions comfortably inside 32 bits
+    bool done = false;
+
+    while (!bail && !done) {
+      // ---- block header (all lanes, uniform): next_block (inflate.mbt:345-379) ----
+      ub.refill();
+      const int final_flag = (int)ub.take(1);
+      const int typ = (int)ub.take(2);
+      if (typ == 3) { bail = true; break; }
+      if (typ == 0) { // stored block (data_block / copy_data, :708-766)
+        const int64_t p = (ub.consumed_bits(in) + 7) >> 3;
+        if (p + 4 > cur_len) { bail = true; break; }
+        const uint32_t sn = (uint32_t)__ldg(in + p) | ((uint32_t)__ldg(in + p + 1) << 8);
+        const uint32_t nn = (uint32_t)__ldg(in + p + 2) | ((uint32_t)__ldg(in + p + 3) << 8);
+        if (nn != ((~sn) & 0xffffu) || p + 4 + sn > cur_len || (uint64_t)opos + sn > cap) { bail = true; break; }
+        const uint32_t sp = (uint32_t)(p + 4);
+        for (uint32_t i = lane; i < sn; i += 32) out[opos + i] = __ldg(in + sp + i);
+        opos += sn;
+        cur_len -= (int64_t)sp + sn;
+        in += sp + sn;
+        ub.init(in, (uint64_t)cur_len);
+        __syncwarp();
+        if (final_flag) done = true;
+        continue;
+      }
+      int mn1 = 0, mx1 = 0, mn2 = 0, mx2 = 0;
+      if (typ == 1) { // fixed_huffman_decoder (:886-939); distances are 5-bit codes
+        for (int i = lane; i < 288; i += 32) sm.lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+        sm.lens[288 + lane] = 5;
+        __syncwarp();
+        warp_canon(sm.lens, 288, sm.lsorted, &sm.tl, &mn1, &mx1);
+        warp_canon(sm.lens + 288, 32, sm.dsorted, &sm.td, &mn2, &mx2);
+      } else { // read_huffman (:429-548)
+        ub.refill();
+        const int nlit = (int)ub.take(5) + 257;
+        const int ndist = (int)ub.take(5) + 1;
+        const int nclen = (int)ub.take(4) + 4;
+        if (nlit > kNumLit || ndist > kNumDist) { bail = true; break; }
+        if (lane < 19) sm.cl_lens[lane] = 0;
+        __syncwarp();
+        for (int i = 0; i < nclen; i++) {
+          ub.refill();
+          const uint32_t v = ub.take(3);
+          if (lane == 0) sm.cl_lens[c3_code_order[i]] = (uint8_t)v;
+        }
+        __syncwarp();
+        int mnc = 0, mxc = 0;
+        if (!warp_canon(sm.cl_lens, 19, sm.dsorted, &sm.td, &mnc, &mxc)) { bail = true; break; }
+        warp_fill_lut(sm.cl, 7, sm.dsorted, &sm.td, mnc, mxc);
+        bool herr = false;
+        const int n = nlit + ndist;
+        int i = 0, prev = 0;
+        while (i < n) {
+          ub.refill();
+          const uint32_t e = sm.cl[ub.peek() & 127];
+          const int len = (int)(e & 15), x = (int)(e >> 4);
+          if (len == 0) { herr = true; break; }
+          ub.drop(len);
+          if (x < 16) {
+            if (lane == 0) sm.lens[i] = (uint8_t)x;
+            prev = x;
+            i++;
+            continue;
+          }
+          int rep, b = 0;
+          if (x == 16) {
+            if (i == 0) { herr = true; break; }
+            b = prev;
+            rep = 3 + (int)ub.take(2);
+          } else if (x == 17) rep = 3 + (int)ub.take(3);
+          else rep = 11 + (int)ub.take(7);
+          if (i + rep > n) { herr = true; break; }
+          for (int k = lane; k < rep; k += 32) sm.lens[i + k] = (uint8_t)b;
+          i += rep;
+          prev = b;
+        }
+        __syncwarp();
+        if (herr) { bail = true; break; }
+        uint8_t dl = 0;
+        if (lane < ndist) dl = sm.lens[nlit + lane];
+        __syncwarp();
+        sm.lens[288 + lane] = (lane < ndist) ? dl : 0;
+        __syncwarp();
+        if (sm.lens[kEob] == 0) { bail = true; break; }
+        if (!warp_canon(sm.lens, nlit, sm.lsorted, &sm.tl, &mn1, &mx1)) { bail = true; break; }
+        if (!warp_canon(sm.lens + 288, ndist, sm.dsorted, &sm.td, &mn2, &mx2)) { bail = true; break; }
+      }
+      warp_fill_lut(sm.lit, kLB, sm.lsorted, &sm.tl, mn1, mx1);
+      warp_fill_lut(sm.dist, kDB, sm.dsorted, &sm.td, mn2, mx2);
+
+      // ---- block body: 32 ranges, speculative starts, fixpoint over the hand-over positions ----
+      const int64_t b0s = ub.consumed_bits(in);
+      if (b0s >= cur_len * 8) { bail = true; break; }
+      const uint32_t b0 = (uint32_t)b0s, bend = (uint32_t)(cur_len * 8);
+      uint32_t R = (bend - b0 + 31u) / 32u;
+      if (R < kMinRange) R = kMinRange;
+      const uint64_t s64 = (uint64_t)b0 + (uint64_t)lane * R;
+      const uint32_t s_nom = s64 < bend ? (uint32_t)s64 : bend;
+      const uint32_t e_i = (s64 + R < bend) ? (uint32_t)(s64 + R) : bend;
+      uint32_t start = s_nom, p = 0, flag = P_OK, n_out = 0, n_rec = 0;
+      bool need = true;
+      for (int round = 0; round < 34; round++) {
+        uint32_t tp, tf, to, tr;
+        decode_ranges<false>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, need, start, e_i, tp, tf, to, tr, nullptr,
+                             0u, nullptr);
+        if (need) { p = tp; flag = tf; n_out = to; n_rec = tr; }
+        const uint32_t pp = __shfl_up_sync(kFull, p, 1);
+        const uint32_t pf = __shfl_up_sync(kFull, flag, 1);
+        const uint32_t ns = lane == 0 ? b0 : (pf == P_OK ? pp : start);
+        need = ns != start;
+        start = ns;
+        if (lane == 0) atomicAdd(&j.counters[5], 1u); // instrumentation: decode rounds
+        if (!__any_sync(kFull, need)) break;
+      }
+      if (lane == 0) atomicAdd(&j.counters[6], 1u); // instrumentation: blocks
+      // the chain is valid up to the first lane that does not hand over; it must have met EOB
+      const unsigned notok = __ballot_sync(kFull, flag != P_OK);
+      if (notok == 0) { bail = true; break; } // no EOB before the end of the input
+      const int f = __ffs(notok) - 1;
+      if (__shfl_sync(kFull, flag, f) != P_EOB) { bail = true; break; }
+      const bool mine = lane <= f;
+      uint32_t xo = mine ? n_out : 0u, xr = mine ? n_rec : 0u;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yo = __shfl_up_sync(kFull, xo, o), yr = __shfl_up_sync(kFull, xr, o);
+        if (lane >= o) { xo += yo; xr += yr; }
+      }
+      const uint32_t tot_o = __shfl_sync(kFull, xo, 31), tot_r = __shfl_sync(kFull, xr, 31);
+      if (tot_o > cap - opos || tot_r > rec_cap - nrec) { bail = true; break; }
+      {
+        uint32_t tp, tf, to, tr;
+        decode_ranges<true>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, mine, start, e_i, tp, tf, to, tr, out,
+                            opos + xo - (mine ? n_out : 0u), rec + nrec + xr - (mine ? n_rec : 0u));
+        const bool bad = mine && (tf == P_BAD || tp != p || to != n_out || tr != n_rec);
+        if (__any_sync(kFull, bad)) { bail = true; break; }
+      }
+      opos += tot_o;
+      nrec += tot_r;
+      // continue after the EOB: re-base the uniform reader there
+      const uint32_t eob = __shfl_sync(kFull, p, f);
+      if ((int64_t)eob > cur_len * 8) { bail = true; break; }
+      in += eob >> 3;
+      cur_len -= (int64_t)(eob >> 3);
+      ub.init(in, (uint64_t)cur_len);
+      ub.refill();
+      ub.drop((int)(eob & 7u));
+      __syncwarp();
+      if (final_flag) done = true;
+    }
+
+    if (!bail && ub.consumed_bits(in) > cur_len * 8) bail = true;
+    if (!bail) {
+      __syncwarp();
+      replay_records(out, rec, nrec, lane);
+    }
+    if (lane == 0) {
+      if (bail) {
+        const uint32_t k = atomicAdd(&j.counters[2], 1u);
+        j.fallback[k] = st32;
+      } else {
+        const int64_t cb = ub.consumed_bits(in);
+        j.out_len[st32] = opos;
+        j.status[st32] = FB200_ST_EOF;
+        j.err_off[st32] = 0;
+        if (j.consumed) j.consumed[st32] = (uint64_t)((int64_t)(in - in0) + ((cb + 7) >> 3));
+      }
+    }
+    __syncwarp();
+    if (j.group_done) { // host-buffer call: publish finished output groups so their D2H copy can start
+      __threadfence();
+      if (lane == 0) {
+        const uint32_t g = st32 / j.group_streams;
+        const uint32_t first = g * j.group_streams;
+        const uint32_t cnt = (uint32_t)(j.nstreams - first < j.group_streams ? j.nstreams - first : j.group_streams);
+        if (atomicAdd(&j.group_done[g], 1u) + 1u == cnt) {
+          __threadfence_system();
+          j.group_flag[g] = 1u;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+} // namespace par
+
+void launch_inflate3(const InflateJob &j, int num_sms, cudaStream_t st)
+{
+  if (j.nstreams == 0) return;
+  static int minb = 0;
+  if (!minb) {
+    const char *e = getenv("FB200_INFLATE_CTAS");
+    minb = e ? atoi(e) : 8;
+    if (minb != 6 && minb != 8 && minb != 12) minb = 8;
+  }
+  const uint64_t want = (j.nstreams + par::kWarps - 1) / par::kWarps;
+  const uint64_t maxg = (uint64_t)num_sms * minb;
+  const unsigned g = (unsigned)(want < maxg ? want : maxg);
+  if (minb == 6) par::k_inflate_par<6><<<g, par::kWarps * 32, 0, st>>>(j);
+  else if (minb == 8) par::k_inflate_par<8><<<g, par::kWarps * 32, 0, st>>>(j);
+  else par::k_inflate_par<12><<<g, par::kWarps * 32, 0, st>>>(j);
+}
+
+void preload_inflate3_kernels()
+{
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, par::k_inflate_par<6>);
+  cudaFuncGetAttributes(&a, par::k_inflate_par<8>);
+  cudaFuncGetAttributes(&a, par::k_inflate_par<12>);
+}
+
+} // namespace fb

@@ -32,6 +32,9 @@ struct DeflateJob {
   // tokens of the block starting at source byte o live at tokens[o .. o+ntok)
   uint32_t *tokens;           // [n_total]
   uint32_t *counters;         // [8] work-stealing counters, zeroed per call
+  // host-buffer calls: number of streams whose bytes have arrived (advanced by the H2D stream after
+  // every chunk); the parse waits on it, so the copy overlaps the kernel.  Null: everything is resident.
+  const uint32_t *avail;
   // output
   uint8_t *dst;
 };
@@ -62,6 +65,11 @@ void launch_fill_seg_off(uint64_t *off, uint64_t nseg, uint64_t seg, uint64_t n,
 // out[i] = in[i] + delta (mod 2^64), i in [0, cnt): re-bases offset arrays for chunked host calls
 void launch_affine_u64(uint64_t *out, const uint64_t *in, uint64_t cnt, uint64_t delta, cudaStream_t st);
 
+void preload_parse_kernels();
+void preload_encode_kernels();
+void preload_inflate_kernels();
+void preload_inflate2_kernels();
+
 struct InflateJob {
   const uint8_t *comp;
   const uint64_t *comp_off; // [nstreams+1]
@@ -74,6 +82,12 @@ struct InflateJob {
   uint64_t *consumed;       // [nstreams] or null
   uint32_t *fallback;       // [nstreams] streams the fast path hands to the exact kernel
   uint32_t *counters;       // [0] fast work counter, [1] exact work counter, [2] fallback count, [3] copy work counter
+  // host-buffer calls (all null / 0 otherwise): streams whose input has arrived; per-group completion
+  // counters and host-visible flags so that finished output groups can be copied back while the kernel runs
+  const uint32_t *avail;
+  uint32_t *group_done;     // [ngroups]
+  volatile uint32_t *group_flag; // [ngroups] mapped pinned host memory
+  uint32_t group_streams;   // streams per group
   // two-kernel fast path (inflate2.cu): recorded back-references
   uint2 *records;           // {dst, len | (dist-1) << 16}
   const uint64_t *rec_off;  // [nstreams+1] record area of each stream
@@ -86,6 +100,10 @@ void launch_inflate(const InflateJob &j, int num_sms, bool fast_v1, cudaStream_t
 // thread-per-stream decode + warp-per-stream copy replay (inflate2.cu)
 // order_hist: device scratch of 1024 uint32
 void launch_inflate2(const InflateJob &j, int num_sms, uint32_t *order_hist, cudaStream_t st);
+// warp-per-stream, lanes decode one block in parallel (inflate3.cu)
+void launch_inflate3(const InflateJob &j, int num_sms, cudaStream_t st);
+void preload_inflate3_kernels();
+void launch_stream_order(const InflateJob &j, uint32_t *order_hist, cudaStream_t st);
 void launch_rec_off(const uint64_t *out_off, uint64_t *rec_off, uint64_t ns, cudaStream_t st);
 
 } // namespace fb

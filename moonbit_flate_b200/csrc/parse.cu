@@ -96,6 +96,11 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
     if (lane == 0) st32 = atomicAdd(counter, 1u);
     st32 = __shfl_sync(kFull, st32, 0);
     if (st32 >= j.nstreams) break;
+    if (j.avail) { // host-buffer call: wait until the H2D stream has delivered this stream's bytes
+      if (lane == 0)
+        while (*(volatile const uint32_t *)j.avail <= st32) __nanosleep(500);
+      __syncwarp();
+    }
     const uint64_t o0 = j.stream_off[st32];
     const uint64_t L = j.stream_off[st32 + 1] - o0;
     const bool is_multi = L >= (uint64_t)kBlockSize + 128;
@@ -143,7 +148,8 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           const int base = s - 1;
           const int pos = base + lane;
           const uint32_t cv = ld32u(srcb + pos);
-          if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + pos + 256));
+          // (never beyond the block: with host-buffer calls the bytes after it may not have arrived yet)
+          if (lane == 0 && pos + 256 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + pos + 256));
           const uint32_t h = hash4(cv);
           T *slot = table + h;
           const T old = *slot;
@@ -504,6 +510,21 @@ __global__ void __launch_bounds__(1024) k_scan_u64(const uint64_t *in, uint64_t 
 void launch_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n, cudaStream_t st)
 {
   k_scan_u64<<<1, 1024, 0, st>>>(in, out, n);
+}
+
+// CUDA loads kernels lazily, and loading one while another kernel spins on a host-fed watermark can
+// deadlock: every kernel of this file is loaded when the context is created.
+void preload_parse_kernels()
+{
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_init_sched);
+  cudaFuncGetAttributes(&a, k_parse<false>);
+  cudaFuncGetAttributes(&a, k_parse<true>);
+  cudaFuncGetAttributes(&a, k_count_blocks);
+  cudaFuncGetAttributes(&a, k_fill_blocks);
+  cudaFuncGetAttributes(&a, k_fill_seg_off);
+  cudaFuncGetAttributes(&a, k_affine_u64);
+  cudaFuncGetAttributes(&a, k_scan_u64);
 }
 
 } // namespace fb
