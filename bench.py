@@ -362,7 +362,7 @@ def main():
     deflate_ms = sum(v for kk, v in st_ms.items() if kk != "inflate")
     inflate_ms = st_ms.get("inflate", 0.0)
     dom = max(st_ms, key=lambda kk: st_ms[kk])
-    kernel_name = {"parse": "k_parse (K1 lz77 parse)", "inflate": "k_inflate (K6)"}.get(dom, dom)
+    kernel_name = {"parse": "k_parse (K1 lz77 parse)", "inflate": "k_inflate_par (K6 inflate)"}.get(dom, dom)
     alg_bytes = nbytes + c_local  # per launch: N + C (deflate) == C + N (inflate), SURVEY 8d
     achieved = alg_bytes / (st_ms[dom] * 1e-3) / 1e9
     traffic = None

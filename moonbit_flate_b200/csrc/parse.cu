@@ -251,7 +251,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
               uint32_t t = cv & 0xffu; // emit_literal (:273-279)
               if ((hitm >> lane) & 1u) // match_token(l + 4 - 3, s - t - 1) (:228-233)
                 t = kMatchType + ((uint32_t)(my_ext + 1) << kLengthShift) + (uint32_t)(pos - cand - 1);
-              tok[ntok + (uint32_t)__popc(emit & lt_mask)] = t;
+              __stcs(&tok[ntok + (uint32_t)__popc(emit & lt_mask)], t);
             }
             ntok += (uint32_t)__popc(emit);
             if (!GTAB) __syncwarp();
@@ -331,7 +331,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         const int s_hit = __shfl_sync(kFull, pos, m);
         const int c = __shfl_sync(kFull, cand, m);
         // emit_literal(src[next_emit:s]) (:207)
-        for (int i = next_emit + lane; i < s_hit; i += 32) tok[ntok + (uint32_t)(i - next_emit)] = __ldg(srcb + i);
+        for (int i = next_emit + lane; i < s_hit; i += 32) __stcs(&tok[ntok + (uint32_t)(i - next_emit)], (uint32_t)__ldg(srcb + i));
         ntok += (uint32_t)(s_hit - next_emit);
         // match_len (:286-307); t < 0 -> 0 (D1, :310-313)
         const int s2 = s_hit + 4, t = c + 4;
@@ -342,7 +342,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           ext = match_tail(srcb, s2, t, s1 - s2, 0, lane);
         }
         if (lane == 0) // match_token(l + 4 - 3, s - t - 1) (:228-233)
-          tok[ntok] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1);
+          __stcs(&tok[ntok], kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1));
         ntok++;
         s = s2 + ext;
         next_emit = s;
@@ -350,7 +350,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         modeM = true;
       }
       // emit_remainder (:152-159)
-      for (int i = next_emit + lane; i < n; i += 32) tok[ntok + (uint32_t)(i - next_emit)] = __ldg(srcb + i);
+      for (int i = next_emit + lane; i < n; i += 32) __stcs(&tok[ntok + (uint32_t)(i - next_emit)], (uint32_t)__ldg(srcb + i));
       ntok += (uint32_t)(n - next_emit);
       if (lane == 0) j.blk_ntok[blk0 + b] = ntok;
       __syncwarp();
@@ -405,10 +405,44 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
     inited = true;
   }
   const int gw = g_parse_gwarps;
+  // keep the global-memory tables resident in L2 (they are hit at random, 2 bytes at a time) while the
+  // source and the token stream flow through
+  static int persist = -1;
+  if (persist < 0) {
+    const char *e = getenv("FB200_PARSE_L2PERSIST");
+    persist = e ? atoi(e) : 1;
+    if (persist && gw) {
+      int dev = 0, maxp = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
+      else persist = 0;
+    }
+  }
+  if (persist && gw) {
+    int dev = 0, maxw = 0, maxp = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    size_t bytes = (size_t)num_sms * gw * kTableSize * 2;
+    if ((size_t)maxw < bytes) bytes = (size_t)maxw;
+    cudaStreamAttrValue av{};
+    av.accessPolicyWindow.base_ptr = g_parse_gtables;
+    av.accessPolicyWindow.num_bytes = bytes;
+    av.accessPolicyWindow.hitRatio = bytes <= (size_t)maxp ? 1.0f : (float)((double)maxp / (double)bytes);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
   k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * 2, st>>>(
       j, j.counters + 0, g_parse_occ_single, g_parse_gtables);
   k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4, st>>>(
       j, j.counters + 1, g_parse_occ_multi, g_parse_gtables);
+  if (persist && gw) {
+    cudaStreamAttrValue av{};
+    av.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
 }
 
 // ------------------------------------------------------------------

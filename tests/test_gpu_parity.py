@@ -280,3 +280,37 @@ def test_host_api_chunk_pipeline(oracle, corpus, monkeypatch):
         assert rc == fb.ERR_DST_TOO_SMALL and need.value == comp2.size
     finally:
         c.close()
+
+
+def test_config3_many_small_streams(ctx, oracle, corpus):
+    """BASELINE configs[2] in small: a batch of independent 1..16 KiB streams (ragged offsets, every class):
+    every GPU stream equals the oracle's on a sample, all of them inflate back bit-exactly, and the decoder
+    consumes exactly each stream."""
+    nstreams = 20000
+    src, off = corpus.fill_var(nstreams, seed=5)
+    comp, doff = ctx.deflate_streams(src, off)
+    assert int(doff[-1]) == comp.size
+    for i in range(0, nstreams, 397):
+        d = src[int(off[i]): int(off[i + 1])].tobytes()
+        assert comp[int(doff[i]): int(doff[i + 1])].tobytes() == oracle.deflate(d), i
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, doff, off)
+    assert (st == 0).all()
+    assert np.array_equal(olen, np.diff(off))
+    assert np.array_equal(cons, np.diff(doff))
+    assert np.array_equal(out, src)
+
+
+@pytest.mark.parametrize("klass", [2, 4, 5, 3])
+def test_config5_worst_cases(ctx, oracle, corpus, klass):
+    """BASELINE configs[4] in small: incompressible random bytes (every block a literal-only Huffman block --
+    the reference never stores, quirk D2) and long-run data (maximum-length matches), 512 segments each."""
+    nseg, seg = 512, 65536
+    src = corpus.fill(nseg, seg, seed=41, klass=klass)
+    comp, off = ctx.deflate_segments(src, seg)
+    for i in range(0, nseg, 61):
+        d = src[i * seg:(i + 1) * seg].tobytes()
+        assert comp[int(off[i]): int(off[i + 1])].tobytes() == oracle.deflate(d), (klass, i)
+    if klass == 2:
+        assert comp.size > src.size  # ~1.001x: dynamic literal-only blocks, no stored data blocks
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, off, np.arange(nseg + 1, dtype=np.uint64) * seg)
+    assert (st == 0).all() and (olen == seg).all() and np.array_equal(out, src)
