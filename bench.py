@@ -56,48 +56,65 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region.  The sampler is started a little early
+    (nvidia-smi needs ~100 ms to come up); every sample carries a timestamp and only those that fall inside
+    [mark_begin, mark_end] are used -- if the region was shorter than one sampling period, the samples of the
+    identical warm-up load right before it are reported and flagged."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.p = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
         self.p.terminate()
         try:
             out, _ = self.p.communicate(timeout=5)
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]),
+                             [nm for nm, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        note = "samples inside the timed region"
+        if not inside:
+            inside = [r for r in rows if self.t0 is None or r[0] <= self.t1][-4:]
+            note = "timed region shorter than the sampling period: last samples of the identical warm-up load"
+        sm = [r[1] for r in inside]
+        reasons = sorted({x for r in inside for x in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "samples": len(sm), "reasons": reasons, "window": note}
 
 
 # ---------------------------------------------------------------------------
@@ -160,7 +177,7 @@ def cpu_baseline(src: np.ndarray, nseg_total: int, budget_s: float = 12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--segments", type=int, default=16384, help="64 KiB segments per GPU (16384 = 1 GiB)")
@@ -271,6 +288,8 @@ def main():
             stage_acc["inflate"] = stage_acc.get("inflate", 0.0) + ctx.last_stage_ms()["inflate"]
 
     # warm-up (untimed) + parity check of the resident result
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step(record=False)
     torch.cuda.synchronize()
@@ -286,19 +305,20 @@ def main():
             assert got == orc.deflate(h_np[i * SEG:(i + 1) * SEG].tobytes()), f"segment {i} differs from the oracle"
 
     # timed region: events on the stream the kernels are launched on
-    sampler = ClockSampler(local_rank)
+    step(record=False)  # same load right before the timed region (also keeps the clocks up for the sampler)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
+    sampler.mark_begin()
     e0.record(lib_stream)
     for _ in range(args.steps):
         step(record=True)
     torch.cuda.synchronize()
     e1.record(lib_stream)
     e1.synchronize()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)

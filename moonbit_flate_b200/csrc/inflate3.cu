@@ -41,6 +41,8 @@ constexpr uint32_t kLitLim = 256u << 4; // table entry = (symbol << 4) | code le
 constexpr uint32_t P_OK = 0, P_EOB = 1, P_BAD = 2;
 constexpr uint32_t kMinRange = 256;     // bits per lane at least
 constexpr int kLaneCopyMax = 24;
+constexpr uint32_t kPrefetchWords = 24;  // lane read-ahead: three 32-byte sectors
+constexpr uint32_t kSyncBits = 1536;   // round-0 run-in of a lane (bits)
 
 struct Tab {
   uint16_t first[16], count[16], offs[16];
@@ -205,14 +207,34 @@ struct LBits {
       wi++;
       nx = ld(wi + 2);
       bo -= 32;
+      // every lane streams through its own range: without this each 32-byte sector is a demand miss, and
+      // with 32 lanes in different places a warp would be waiting on one of them at nearly every step
+      if ((wi & 7u) == 0u && wi + kPrefetchWords < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + kPrefetchWords));
     }
   }
   __device__ __forceinline__ uint32_t abit() const { return (wi << 5) + (uint32_t)bo; }
 };
 
+// shared-memory loads by 32-bit shared address (the tables are reached through a reference, which would
+// otherwise cost a generic-to-shared conversion per access)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
+{
+  unsigned short v;
+  asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
 // Every lane with `run` decodes from bit `start` until it reaches bit `e` (or EOB, or something invalid);
 // bit positions are relative to `in`.  WRITE: literals go to out[obase + ...], back-references to rec[...]
-// with absolute destinations.
+// with absolute destinations.  One symbol per step and lane; the step is straight-line code, and its two
+// optional parts (a code longer than the direct table, a length/distance pair) are entered by the whole
+// warp when any lane needs them.
 template <bool WRITE>
 __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_len_tab, const uint32_t *s_dist_tab,
                                               const uint8_t *in, int64_t cur_len, uint32_t bend, bool run,
@@ -220,6 +242,10 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
                                               uint32_t &n_out, uint32_t &n_rec, uint8_t *out, uint32_t obase,
                                               uint2 *rec)
 {
+  const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(sm.lit);
+  const uint32_t dist_sa = (uint32_t)__cvta_generic_to_shared(sm.dist);
+  const uint32_t ltab_sa = (uint32_t)__cvta_generic_to_shared(s_len_tab);
+  const uint32_t dtab_sa = (uint32_t)__cvta_generic_to_shared(s_dist_tab);
   const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
   const uint32_t *wbase = reinterpret_cast<const uint32_t *>(in - lead);
   const uint32_t lead_bits = lead * 8u;
@@ -227,25 +253,31 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
   lb.init(wbase, (uint32_t)((cur_len + lead + 3) >> 2), (run ? start : 0u) + lead_bits);
   const uint32_t e_abs = e + lead_bits, bend_abs = bend + lead_bits;
   uint32_t flag = P_OK, cnt_out = 0, cnt_rec = 0;
+  uint8_t *op = out + obase;
   bool act = run && start < e;
   while (__any_sync(kFull, act)) {
     const uint32_t bits = lb.peek();
-    uint32_t e0 = act ? sm.lit[bits & ((1u << kLB) - 1u)] : 1u;
-    if (__any_sync(kFull, e0 == 0)) {
-      if (e0 == 0) e0 = canon_long(bits, kLB + 1, &sm.tl, sm.lsorted);
+    uint32_t e0 = lds_u16(lit_sa + ((bits & ((1u << kLB) - 1u)) << 1));
+    if (__any_sync(kFull, act && e0 == 0)) {
+      if (act && e0 == 0) e0 = canon_long(bits, kLB + 1, &sm.tl, sm.lsorted);
     }
     const uint32_t cl = e0 & 15u, sym = e0 >> 4;
-    const bool is_len = act && sym > 256u && sym < (uint32_t)kNumLit;
-    uint32_t length = 0;
+    const bool is_len = act && (sym - 257u) < 29u;
+    uint32_t adv = cl, length = 0;
+    if (__any_sync(kFull, is_len)) {
+      if (is_len) {
+        const uint32_t lt = lds_u32(ltab_sa + ((sym - 257u) << 2));
+        const uint32_t xb = lt >> 16;
+        length = (lt & 0xffffu) + ((bits >> cl) & ((1u << xb) - 1u));
+        adv = cl + xb;
+      }
+    }
     if (act) {
       if (e0 == 0 || sym >= (uint32_t)kNumLit) { flag = P_BAD; act = false; }
       else {
-        const uint32_t lt = is_len ? s_len_tab[sym - 257u] : 0u;
-        const uint32_t xb = lt >> 16;
-        length = (lt & 0xffffu) + ((bits >> cl) & ((1u << xb) - 1u));
-        lb.drop((int)(cl + xb));
+        lb.drop((int)adv);
         if (sym < 256u) {
-          if (WRITE) out[obase + cnt_out] = (uint8_t)sym;
+          if (WRITE) op[cnt_out] = (uint8_t)sym;
           cnt_out++;
         } else if (sym == 256u) { flag = P_EOB; act = false; }
       }
@@ -253,12 +285,12 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
     if (__any_sync(kFull, is_len && act)) {
       if (is_len && act) {
         const uint32_t dbits = lb.peek();
-        uint32_t d = sm.dist[dbits & ((1u << kDB) - 1u)];
+        uint32_t d = lds_u16(dist_sa + ((dbits & ((1u << kDB) - 1u)) << 1));
         if (d == 0) d = canon_long(dbits, kDB + 1, &sm.td, sm.dsorted);
         if (d == 0 || (d >> 4) >= (uint32_t)kNumDist) { flag = P_BAD; act = false; }
         else {
           const uint32_t dl = d & 15u;
-          const uint32_t dt = s_dist_tab[d >> 4];
+          const uint32_t dt = lds_u32(dtab_sa + ((d >> 4) << 2));
           const uint32_t dxb = dt >> 16;
           lb.drop((int)(dl + dxb));
           if (WRITE) {
@@ -474,6 +506,13 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
       }
       warp_fill_lut(sm.lit, kLB, sm.lsorted, &sm.tl, mn1, mx1);
       warp_fill_lut(sm.dist, kDB, sm.dsorted, &sm.td, mn2, mx2);
+      // a code whose symbols nearly all share one length (incompressible data) barely self-synchronises
+      bool flat_code;
+      {
+        const uint32_t c = lane < 16 ? sm.tl.count[lane] : 0u;
+        const uint32_t mxc = __reduce_max_sync(kFull, c), tot = __reduce_add_sync(kFull, c);
+        flat_code = mxc * 10u >= tot * 8u;
+      }
 
       // ---- block body: 32 ranges, speculative starts, fixpoint over the hand-over positions ----
       const int64_t b0s = ub.consumed_bits(in);
@@ -484,7 +523,12 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
       const uint64_t s64 = (uint64_t)b0 + (uint64_t)lane * R;
       const uint32_t s_nom = s64 < bend ? (uint32_t)s64 : bend;
       const uint32_t e_i = (s64 + R < bend) ? (uint32_t)(s64 + R) : bend;
+      // Round 0 only has to find where each lane leaves its range, and a wrong start falls onto true symbol
+      // boundaries within a few dozen symbols: every lane decodes just the last kSyncBits of their range (the
+      // whole range when most codes have the same length, which synchronises poorly).  A lane that did not
+      // synchronise is caught by the fixpoint below like any other wrong hand-over.
       uint32_t start = s_nom, p = 0, flag = P_OK, n_out = 0, n_rec = 0;
+      if (!flat_code && e_i - s_nom > kSyncBits) start = e_i - kSyncBits; // lane 0 too: its full pass is round 1
       bool need = true;
       for (int round = 0; round < 34; round++) {
         uint32_t tp, tf, to, tr;
