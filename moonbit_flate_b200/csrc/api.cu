@@ -73,7 +73,12 @@ struct fb200_ctx {
   volatile uint32_t *h_flags = nullptr; // mapped pinned: inflate output groups finished on the device
   DevBuf group_done;
   static constexpr int kMaxChunks = 4096;
-  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr, s_post = nullptr;
+  cudaEvent_t e_setup = nullptr, e_post = nullptr;
+  DevBuf queue;
+  // FB200_POST_OVERLAP=1 runs K2 + K3 (k_post) beside the parse.  Measured: the co-resident CTAs need a larger
+  // shared-memory carve-out (FB200_PARSE_CARVEOUT=77), and the L1 the parse loses costs as much as is hidden.
+  bool post_overlap = false;
   cudaEvent_t e_in[2] = {}, e_comp[2] = {}, e_out[2] = {};
   uint64_t chunk_bytes = 32ull << 20;
   uint64_t *pinned = nullptr; // small pinned read-back area
@@ -140,6 +145,10 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   }
   cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->s_post, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->e_setup, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->e_post, cudaEventDisableTiming);
+  if (const char *e = getenv("FB200_POST_OVERLAP")) ctx->post_overlap = atoi(e) != 0;
   for (int i = 0; i < 2; i++) {
     cudaEventCreateWithFlags(&ctx->e_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->e_comp[i], cudaEventDisableTiming);
@@ -189,6 +198,10 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
     if (ctx->e_out[i]) cudaEventDestroy(ctx->e_out[i]);
   }
   ctx->group_done.release();
+  ctx->queue.release();
+  if (ctx->s_post) cudaStreamDestroy(ctx->s_post);
+  if (ctx->e_setup) cudaEventDestroy(ctx->e_setup);
+  if (ctx->e_post) cudaEventDestroy(ctx->e_post);
   if (ctx->d_wm) cudaFree(ctx->d_wm);
   if (ctx->wm_vals) cudaFreeHost(ctx->wm_vals);
   if (ctx->h_flags) cudaFreeHost((void *)ctx->h_flags);
@@ -293,16 +306,33 @@ static int deflate_phase_a_launch(fb200_ctx *ctx, const uint8_t *d_src, const ui
   CK(cudaMemsetAsync(j.blk_bits, 0, nbp * 4, st));
 
   launch_fill_blocks(j, st);
+  if (ctx->post_overlap) {
+    CK(ctx->queue.ensure(nbp * 4));
+    j.queue = ctx->queue.as<uint32_t>();
+    CK(cudaMemsetAsync(j.queue, 0, nbp * 4, st));
+  }
   ctx->stage_end(FB200_STAGE_SETUP);
+  if (ctx->post_overlap) { // K2 + K3 run beside the parse, block by block as the parse finishes them
+    CK(cudaEventRecord(ctx->e_setup, st));
+    CK(cudaStreamWaitEvent(ctx->s_post, ctx->e_setup, 0));
+  }
   ctx->stage_begin(FB200_STAGE_PARSE);
   launch_parse(j, ctx->num_sms, st);
   ctx->stage_end(FB200_STAGE_PARSE);
-  ctx->stage_begin(FB200_STAGE_HISTOGRAM);
-  launch_histogram(j, st);
-  ctx->stage_end(FB200_STAGE_HISTOGRAM);
-  ctx->stage_begin(FB200_STAGE_BUILD);
-  launch_build_codes(j, ctx->num_sms, st);
-  ctx->stage_end(FB200_STAGE_BUILD);
+  if (ctx->post_overlap) {
+    launch_post(j, ctx->num_sms, ctx->s_post);
+    CK(cudaEventRecord(ctx->e_post, ctx->s_post));
+    ctx->stage_begin(FB200_STAGE_BUILD); // = what the code construction still costs after the parse has ended
+    CK(cudaStreamWaitEvent(st, ctx->e_post, 0));
+    ctx->stage_end(FB200_STAGE_BUILD);
+  } else {
+    ctx->stage_begin(FB200_STAGE_HISTOGRAM);
+    launch_histogram(j, st);
+    ctx->stage_end(FB200_STAGE_HISTOGRAM);
+    ctx->stage_begin(FB200_STAGE_BUILD);
+    launch_build_codes(j, ctx->num_sms, st);
+    ctx->stage_end(FB200_STAGE_BUILD);
+  }
   ctx->stage_begin(FB200_STAGE_LAYOUT);
   launch_layout(j, st);
   launch_scan_u64(j.stream_bytes, j.dst_off, ns, st);

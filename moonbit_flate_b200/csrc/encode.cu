@@ -128,6 +128,88 @@ void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------
+// K2 + K3 fused, one warp per block, consuming the completion queue of the parse: the block policy and
+// histogram (k_histogram) go straight into the warp's shared-memory scratch, then the codes are built.
+// The kernel is co-resident with the (latency-bound) parse, so code construction costs no time of its own.
+constexpr int kPostWarpsMax = 4;
+
+__global__ void __launch_bounds__(kPostWarpsMax * 32) k_post(DeflateJob j)
+{
+  extern __shared__ __align__(16) uint8_t build_smem[];
+  HuffScratch &S = reinterpret_cast<HuffScratch *>(build_smem)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&j.counters[9], 1u);
+    t = __shfl_sync(kFull, t, 0);
+    if (t >= j.nblocks) break;
+    uint32_t v = 0;
+    if (lane == 0)
+      while ((v = *(volatile uint32_t *)&j.queue[t]) == 0) __nanosleep(300);
+    v = __shfl_sync(kFull, v, 0);
+    const uint64_t blk = v - 1u;
+    const BlockRef r = block_ref(j, blk);
+    const uint32_t n = r.n;
+    const uint32_t ntok = __ldcg(&j.blk_ntok[blk]);
+    int kind;
+    if (n <= 16) kind = kKindStored;                 // deflate.mbt:248-249
+    else if (n < 128) kind = kKindHuff;              // :250-252
+    else kind = (ntok > n - (n >> 4)) ? kKindHuff : kKindDynamic; // :266
+    if (kind == kKindStored) {
+      if (lane == 0) j.blk_kind[blk] = (uint8_t)kind;
+      continue;
+    }
+    for (int i = lane; i < 320; i += 32) S.freq[i] = 0;
+    __syncwarp();
+    if (kind == kKindDynamic) {
+      const uint32_t *tok = j.tokens + r.src_off;
+      for (uint32_t i = lane; i < ntok; i += 32) {
+        const uint32_t tk = __ldcg(tok + i);
+        if (tk < kMatchType) atomicAdd(&S.freq[tk], 1u);
+        else {
+          int lc, nb, oc;
+          uint32_t ex;
+          length_code_of((tk - kMatchType) >> kLengthShift, lc, nb, ex);
+          offset_code_of(tk & kOffsetMask, oc, nb, ex);
+          atomicAdd(&S.freq[kLenCodesStart + lc], 1u);
+          atomicAdd(&S.freq[kNumLit + oc], 1u);
+        }
+      }
+    } else {
+      const uint8_t *src = j.src + r.src_off;
+      for (uint32_t i = lane; i < n; i += 32) atomicAdd(&S.freq[__ldg(src + i)], 1u);
+    }
+    __syncwarp();
+    if (lane == 0) S.freq[kEob] = 1; // EOB: pushed token 256 (hbw:507) / literal_freq[256] = 1 (hbw:754)
+    __syncwarp();
+    const BlockBuild res = build_block_warp(nullptr, kind, n, j.blk_code + blk * kFreqStride, j.blk_hdr + blk * kHdrWords, S);
+    if (lane == 0) {
+      j.blk_kind[blk] = (uint8_t)res.kind;
+      j.blk_hdr_nbits[blk] = res.hdr_nbits;
+      j.blk_bits[blk] = res.blk_bits;
+    }
+    __syncwarp();
+  }
+}
+
+void launch_post(const DeflateJob &j, int num_sms, cudaStream_t st)
+{
+  if (j.nblocks == 0) return;
+  static bool inited = false;
+  static int warps = 3;
+  if (!inited) {
+    const char *e = getenv("FB200_POST_WARPS");
+    if (e && atoi(e) >= 1 && atoi(e) <= kPostWarpsMax) warps = atoi(e);
+    cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostWarpsMax * (int)sizeof(HuffScratch));
+    inited = true;
+  }
+  const int smem = warps * (int)sizeof(HuffScratch);
+  uint64_t want = (j.nblocks + warps - 1) / warps;
+  unsigned g = (unsigned)(want < (uint64_t)num_sms ? want : (uint64_t)num_sms);
+  k_post<<<g, warps * 32, smem, st>>>(j);
+}
+
+// ------------------------------------------------------------------
 // layout: one thread per stream walks its blocks (bit-contiguous except for
 // stored blocks, which pad to a byte after their 3 header bits, hbw:483-486).
 __global__ void k_layout(DeflateJob j)
@@ -349,6 +431,7 @@ void preload_encode_kernels()
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_histogram);
   cudaFuncGetAttributes(&a, k_build_codes);
+  cudaFuncGetAttributes(&a, k_post);
   cudaFuncGetAttributes(&a, k_layout);
   cudaFuncGetAttributes(&a, k_pack);
   cudaFuncGetAttributes(&a, k_trailer);

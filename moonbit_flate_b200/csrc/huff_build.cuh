@@ -365,7 +365,7 @@ FB_HD inline BlockBuild build_block_warp(const uint32_t *gfreq, int kind, uint32
   res.blk_bits = 0;
   int last_lit = 0, last_off = -1;
   FB_PFOR(i, 320) {
-    const uint32_t f = i < kNumLit + kNumDist ? gfreq[i] : 0u;
+    const uint32_t f = i < kNumLit + kNumDist ? (gfreq ? gfreq[i] : S.freq[i]) : 0u;
     S.freq[i] = f;
     if (f) {
       if (i < kNumLit) { if (i > last_lit) last_lit = i; }

@@ -35,6 +35,10 @@ struct DeflateJob {
   // host-buffer calls: number of streams whose bytes have arrived (advanced by the H2D stream after
   // every chunk); the parse waits on it, so the copy overlaps the kernel.  Null: everything is resident.
   const uint32_t *avail;
+  // finished blocks, in completion order (entry = block index + 1; counters[8] = tail, counters[9] = head):
+  // the parse publishes every block here so that k_post can build its codes while later blocks are still
+  // being parsed.  Null: K2/K3 run as separate kernels after the parse.
+  uint32_t *queue;
   // output
   uint8_t *dst;
 };
@@ -52,6 +56,8 @@ void launch_histogram(const DeflateJob &j, cudaStream_t st);
 // K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,
 //     huffman-bit-writer.mbt:241-471)
 void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st);
+// K2 + K3 per block, fed by DeflateJob::queue; runs beside the parse on its own stream
+void launch_post(const DeflateJob &j, int num_sms, cudaStream_t st);
 // layout: per-stream bit offsets, stream sizes, output offsets
 void launch_layout(const DeflateJob &j, cudaStream_t st);
 // K4: bit packing (huffman-bit-writer.mbt:596-824, :474-487) + stream trailers

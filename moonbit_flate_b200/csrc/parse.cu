@@ -84,6 +84,18 @@ __device__ __forceinline__ int match_tail(const uint8_t *srcb, int s2, int t, in
   return a;
 }
 
+// hands a finished block (tokens + count written, or nothing to parse) to k_post
+__device__ __forceinline__ void publish_block(const DeflateJob &j, uint64_t blk, int lane)
+{
+  if (!j.queue) return;
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t t = atomicAdd(&j.counters[8], 1u);
+    *(volatile uint32_t *)&j.queue[t] = (uint32_t)blk + 1u;
+  }
+}
+
 template <bool MULTI, typename T, bool GTAB>
 __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table)
 {
@@ -104,7 +116,11 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
     const uint64_t o0 = j.stream_off[st32];
     const uint64_t L = j.stream_off[st32 + 1] - o0;
     const bool is_multi = L >= (uint64_t)kBlockSize + 128;
-    if (is_multi != MULTI || L < 128) continue;
+    if (is_multi != MULTI) continue;
+    if (L < 128) { // nothing to parse: at most one small block
+      if (L > 0) publish_block(j, j.stream_blk0[st32], lane);
+      continue;
+    }
 
     // DeflateFast::new (:111-117): empty table
     {
@@ -117,7 +133,8 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
 
     const uint64_t blk0 = j.stream_blk0[st32];
     const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
-    for (uint32_t b = 0; b < nblk; b++) {
+    uint32_t b = 0;
+    for (; b < nblk; b++) {
       const uint64_t boff = (uint64_t)b * kBlockSize;
       const int n = (int)((L - boff) < (uint64_t)kBlockSize ? (L - boff) : (uint64_t)kBlockSize);
       if (n < 128) break; // small tail: not parsed (deflate.mbt:244-257)
@@ -354,7 +371,9 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
       ntok += (uint32_t)(n - next_emit);
       if (lane == 0) j.blk_ntok[blk0 + b] = ntok;
       __syncwarp();
+      publish_block(j, blk0 + b, lane);
     }
+    for (; b < nblk; b++) publish_block(j, blk0 + b, lane); // small tail block
   }
 }
 
@@ -386,11 +405,11 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
   static bool inited = false;
   if (!inited) {
     const char *e = getenv("FB200_PARSE_WARPS");
-    int w = e ? atoi(e) : 4;
+    int w = e ? atoi(e) : 6;
     if (w < 0) w = 0;
     if (w > 7) w = 7;
     const char *g = getenv("FB200_PARSE_GWARPS");
-    int gw = g ? atoi(g) : 20;
+    int gw = g ? atoi(g) : 18;
     if (gw < 0) gw = 0;
     if (gw > 25) gw = 25;
     if (w + gw == 0) w = 1;
@@ -402,6 +421,13 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
                          g_parse_occ_single * kTableSize * 2);
     cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_parse_occ_multi * kTableSize * 4);
+    // leave room in the shared-memory carve-out for the co-resident k_post CTAs (K2 + K3 beside the parse)
+    const char *co = getenv("FB200_PARSE_CARVEOUT");
+    const int pct = co ? atoi(co) : 0; // 0: driver default (smallest carve-out that fits: most L1, which the parse needs)
+    if (pct > 0) {
+      cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     inited = true;
   }
   const int gw = g_parse_gwarps;
