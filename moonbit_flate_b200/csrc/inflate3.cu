@@ -316,6 +316,60 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
   n_rec = cnt_rec;
 }
 
+// The same for a block whose code has no length symbols (HLIT = 257: the literal-only blocks the encoder
+// emits for incompressible data, which resynchronise poorly and therefore run many rounds): nothing but
+// literals and EOB, two symbols per step.
+template <bool WRITE>
+__device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t *in, int64_t cur_len, uint32_t bend,
+                                                  bool run, uint32_t start, uint32_t e, uint32_t &p_out,
+                                                  uint32_t &flag_out, uint32_t &n_out, uint8_t *out, uint32_t obase)
+{
+  const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(sm.lit);
+  const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
+  const uint32_t *wbase = reinterpret_cast<const uint32_t *>(in - lead);
+  const uint32_t lead_bits = lead * 8u;
+  LBits lb;
+  lb.init(wbase, (uint32_t)((cur_len + lead + 3) >> 2), (run ? start : 0u) + lead_bits);
+  const uint32_t e_abs = e + lead_bits, bend_abs = bend + lead_bits;
+  uint32_t flag = P_OK, cnt_out = 0;
+  uint8_t *op = out + obase;
+  bool act = run && start < e;
+  while (__any_sync(kFull, act)) {
+    const uint32_t bits = lb.peek();
+    uint32_t e0 = lds_u16(lit_sa + ((bits & ((1u << kLB) - 1u)) << 1));
+    if (__any_sync(kFull, act && e0 == 0)) {
+      if (act && e0 == 0) e0 = canon_long(bits, kLB + 1, &sm.tl, sm.lsorted);
+    }
+    if (act) {
+      const uint32_t c0 = e0 & 15u, s0 = e0 >> 4;
+      if (e0 == 0 || s0 > 256u) { flag = P_BAD; act = false; }
+      else if (s0 == 256u) { lb.drop((int)c0); flag = P_EOB; act = false; }
+      else {
+        // second symbol from the same 32-bit peek, if the first one leaves the lane inside its range and the
+        // second is a literal of the direct table (anything else waits for the next step)
+        const uint32_t e1 = lds_u16(lit_sa + (((bits >> c0) & ((1u << kLB) - 1u)) << 1));
+        const uint32_t c1 = e1 & 15u, s1 = e1 >> 4;
+        const uint32_t ab0 = lb.abit() + c0;
+        const bool two = e1 != 0 && s1 < 256u && ab0 < e_abs && ab0 <= bend_abs;
+        if (WRITE) {
+          op[cnt_out] = (uint8_t)s0;
+          if (two) op[cnt_out + 1] = (uint8_t)s1;
+        }
+        cnt_out += two ? 2u : 1u;
+        lb.drop((int)(two ? c0 + c1 : c0));
+      }
+    }
+    if (act) {
+      const uint32_t ab = lb.abit();
+      if (ab > bend_abs) { flag = P_BAD; act = false; } // ran past the end of the input
+      else if (ab >= e_abs) act = false;
+    }
+  }
+  p_out = (run && start < e) ? lb.abit() - lead_bits : start;
+  flag_out = flag;
+  n_out = cnt_out;
+}
+
 // Replays records [0, nrec) of one stream in order.
 __device__ void replay_records(uint8_t *out, const uint2 *rec, uint32_t nrec, int lane)
 {
@@ -443,6 +497,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
         continue;
       }
       int mn1 = 0, mx1 = 0, mn2 = 0, mx2 = 0;
+      bool lit_only = false;
       if (typ == 1) { // fixed_huffman_decoder (:886-939); distances are 5-bit codes
         for (int i = lane; i < 288; i += 32) sm.lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
         sm.lens[288 + lane] = 5;
@@ -455,6 +510,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
         const int ndist = (int)ub.take(5) + 1;
         const int nclen = (int)ub.take(4) + 4;
         if (nlit > kNumLit || ndist > kNumDist) { bail = true; break; }
+        lit_only = nlit == 257; // no length symbols in the code
         if (lane < 19) sm.cl_lens[lane] = 0;
         __syncwarp();
         for (int i = 0; i < nclen; i++) {
@@ -531,9 +587,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
       if (!flat_code && e_i - s_nom > kSyncBits) start = e_i - kSyncBits; // lane 0 too: its full pass is round 1
       bool need = true;
       for (int round = 0; round < 34; round++) {
-        uint32_t tp, tf, to, tr;
-        decode_ranges<false>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, need, start, e_i, tp, tf, to, tr, nullptr,
-                             0u, nullptr);
+        uint32_t tp, tf, to, tr = 0;
+        if (lit_only) decode_ranges_lit<false>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u);
+        else decode_ranges<false>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, need, start, e_i, tp, tf, to, tr,
+                                  nullptr, 0u, nullptr);
         if (need) { p = tp; flag = tf; n_out = to; n_rec = tr; }
         const uint32_t pp = __shfl_up_sync(kFull, p, 1);
         const uint32_t pf = __shfl_up_sync(kFull, flag, 1);
@@ -558,9 +615,13 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
       const uint32_t tot_o = __shfl_sync(kFull, xo, 31), tot_r = __shfl_sync(kFull, xr, 31);
       if (tot_o > cap - opos || tot_r > rec_cap - nrec) { bail = true; break; }
       {
-        uint32_t tp, tf, to, tr;
-        decode_ranges<true>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, mine, start, e_i, tp, tf, to, tr, out,
-                            opos + xo - (mine ? n_out : 0u), rec + nrec + xr - (mine ? n_rec : 0u));
+        uint32_t tp, tf, to, tr = 0;
+        if (lit_only)
+          decode_ranges_lit<true>(sm, in, cur_len, bend, mine, start, e_i, tp, tf, to, out,
+                                  opos + xo - (mine ? n_out : 0u));
+        else
+          decode_ranges<true>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, mine, start, e_i, tp, tf, to, tr, out,
+                              opos + xo - (mine ? n_out : 0u), rec + nrec + xr - (mine ? n_rec : 0u));
         const bool bad = mine && (tf == P_BAD || tp != p || to != n_out || tr != n_rec);
         if (__any_sync(kFull, bad)) { bail = true; break; }
       }

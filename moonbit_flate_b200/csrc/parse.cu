@@ -51,6 +51,10 @@ __global__ void k_init_sched()
 }
 
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef FB_GTAB_PREFETCH
+#define FB_GTAB_PREFETCH 0 // measured: no gain (19.8 vs 19.4 ms per GiB)
+#endif
+constexpr bool kGtabPrefetch = FB_GTAB_PREFETCH != 0;
 
 // match_len tail (deflate-fast.mbt:286-307): number of equal bytes of src[s2..] and src[t..], at most a,
 // given that the first `from` already matched.  32 bytes per step; long matches take four steps per
@@ -174,6 +178,10 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           unsigned conf;
           if (GTAB) { // table in global memory: no dependent read-back, compare buckets across lanes instead
             conf = __ballot_sync(kFull, (__match_any_sync(kFull, h) & lt_mask) != 0);
+            // the buckets of the next 32 positions are very likely needed by the next batch(es): pull them
+            // into L1 now, so that the table read above is not a second serial trip to L2 / DRAM
+            if (kGtabPrefetch && pos + 32 + 8 <= s_limit)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(table + hash4(ld32u(srcb + pos + 32))));
           } else {
             __syncwarp();
             *slot = mine;
