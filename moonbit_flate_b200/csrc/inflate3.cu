@@ -274,12 +274,27 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
     }
     if (act) {
       if (e0 == 0 || sym >= (uint32_t)kNumLit) { flag = P_BAD; act = false; }
-      else {
+      else if (sym < 256u) {
+        // a second literal from the same peek, if the first leaves the lane inside its range and the next
+        // code is a literal of the direct table (anything else waits for the next step)
+        const uint32_t e1 = lds_u16(lit_sa + (((bits >> cl) & ((1u << kLB) - 1u)) << 1));
+        const uint32_t c1 = e1 & 15u, s1 = e1 >> 4;
+        const uint32_t ab0 = lb.abit() + cl;
+        const bool two = e1 != 0 && s1 < 256u && ab0 < e_abs && ab0 <= bend_abs;
+        const uint32_t e2 = lds_u16(lit_sa + (((bits >> (cl + c1)) & ((1u << kLB) - 1u)) << 1));
+        const uint32_t c2 = e2 & 15u, s2 = e2 >> 4;
+        const uint32_t ab1 = ab0 + c1;
+        const bool three = two && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
+        if (WRITE) {
+          op[cnt_out] = (uint8_t)sym;
+          if (two) op[cnt_out + 1] = (uint8_t)s1;
+          if (three) op[cnt_out + 2] = (uint8_t)s2;
+        }
+        cnt_out += 1u + (two ? 1u : 0u) + (three ? 1u : 0u);
+        lb.drop((int)(cl + (two ? c1 : 0u) + (three ? c2 : 0u)));
+      } else {
         lb.drop((int)adv);
-        if (sym < 256u) {
-          if (WRITE) op[cnt_out] = (uint8_t)sym;
-          cnt_out++;
-        } else if (sym == 256u) { flag = P_EOB; act = false; }
+        if (sym == 256u) { flag = P_EOB; act = false; }
       }
     }
     if (__any_sync(kFull, is_len && act)) {
@@ -318,7 +333,7 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
 
 // The same for a block whose code has no length symbols (HLIT = 257: the literal-only blocks the encoder
 // emits for incompressible data, which resynchronise poorly and therefore run many rounds): nothing but
-// literals and EOB, two symbols per step.
+// literals and EOB, up to three symbols per step.
 template <bool WRITE>
 __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t *in, int64_t cur_len, uint32_t bend,
                                                   bool run, uint32_t start, uint32_t e, uint32_t &p_out,
@@ -351,12 +366,17 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
         const uint32_t c1 = e1 & 15u, s1 = e1 >> 4;
         const uint32_t ab0 = lb.abit() + c0;
         const bool two = e1 != 0 && s1 < 256u && ab0 < e_abs && ab0 <= bend_abs;
+        const uint32_t e2 = lds_u16(lit_sa + (((bits >> (c0 + c1)) & ((1u << kLB) - 1u)) << 1));
+        const uint32_t c2 = e2 & 15u, s2 = e2 >> 4;
+        const uint32_t ab1 = ab0 + c1;
+        const bool three = two && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
         if (WRITE) {
           op[cnt_out] = (uint8_t)s0;
           if (two) op[cnt_out + 1] = (uint8_t)s1;
+          if (three) op[cnt_out + 2] = (uint8_t)s2;
         }
-        cnt_out += two ? 2u : 1u;
-        lb.drop((int)(two ? c0 + c1 : c0));
+        cnt_out += 1u + (two ? 1u : 0u) + (three ? 1u : 0u);
+        lb.drop((int)(c0 + (two ? c1 : 0u) + (three ? c2 : 0u)));
       }
     }
     if (act) {
