@@ -205,3 +205,46 @@ class HostModel:
         bb = C.c_uint32()
         k = self.L.fbm_build_block(f.ctypes.data, kind, n, codes.ctypes.data, hdr.ctypes.data, C.byref(hb), C.byref(bb))
         return k, codes, hdr, hb.value, bb.value
+
+
+def fuzz_streams(rng, count):
+    """Structured random inputs: small alphabets, periodic data with noise, copies at every distance class,
+    long runs interrupted at random places -- the shapes that stress hash collisions, the skip heuristic, the
+    32768-byte distance limit, the 258-byte match cap and the 15/16 literal rule."""
+    out = []
+    for k in range(count):
+        n = int(rng.choice([130, 200, 1000, 5000, 20000, 65535, 66000, 70000])) + int(rng.integers(0, 200))
+        kind = k % 7
+        if kind == 0:
+            a = rng.integers(0, int(rng.integers(2, 6)), n, dtype=np.uint8)
+        elif kind == 1:
+            period = int(rng.integers(1, 300))
+            a = np.tile(rng.integers(0, 256, period, dtype=np.uint8), n // period + 1)[:n].copy()
+            noise = rng.random(n) < rng.choice([0.0, 0.001, 0.01, 0.05])
+            a[noise] = rng.integers(0, 256, int(noise.sum()), dtype=np.uint8)
+        elif kind == 2:
+            a = rng.integers(0, 256, n, dtype=np.uint8)
+            for _ in range(int(rng.integers(1, 60))):
+                ln = int(rng.integers(4, 600))
+                src = int(rng.integers(0, max(1, n - ln)))
+                dist = int(rng.choice([1, 2, 3, 7, 255, 256, 4095, 32767, 32768, 32769, 40000]))
+                dst = src + dist
+                if dst + ln <= n:
+                    a[dst:dst + ln] = a[src:src + ln]
+        elif kind == 3:
+            a = np.repeat(rng.integers(0, 256, n // 50 + 1, dtype=np.uint8), rng.integers(1, 600, n // 50 + 1))[:n]
+            a = np.resize(a, n)
+        elif kind == 4:
+            words = [bytes(rng.integers(97, 123, int(rng.integers(1, 12)), dtype=np.uint8)) for _ in range(int(rng.integers(2, 400)))]
+            s = b" ".join(words[int(i)] for i in rng.integers(0, len(words), n // 4 + 1))
+            a = np.frombuffer(s[:n].ljust(n, b"."), dtype=np.uint8)
+        elif kind == 5:
+            a = (np.arange(n) * int(rng.integers(1, 7)) % int(rng.integers(2, 257))).astype(np.uint8)
+        else:
+            base = rng.integers(0, 256, 64, dtype=np.uint8)
+            a = base[rng.integers(0, 64, n)]
+            a[:: int(rng.integers(2, 50))] = 0
+        out.append(np.ascontiguousarray(a, dtype=np.uint8).tobytes())
+    return out
+
+

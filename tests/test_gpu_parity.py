@@ -5,7 +5,7 @@ import zlib
 import numpy as np
 import pytest
 
-from helpers import BLK_DYNAMIC, Corpus, Oracle
+from helpers import BLK_DYNAMIC, Corpus, Oracle, fuzz_streams
 
 pytestmark = pytest.mark.gpu
 
@@ -314,3 +314,17 @@ def test_config5_worst_cases(ctx, oracle, corpus, klass):
         assert comp.size > src.size  # ~1.001x: dynamic literal-only blocks, no stored data blocks
     out, olen, st, eo, cons = ctx.inflate_batch(comp, off, np.arange(nseg + 1, dtype=np.uint64) * seg)
     assert (st == 0).all() and (olen == seg).all() and np.array_equal(out, src)
+
+
+def test_fuzz_deflate_inflate_against_oracle(ctx, oracle):
+    rng = np.random.default_rng(20260101)
+    datas = fuzz_streams(rng, 420)
+    src = np.frombuffer(b"".join(datas), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(d) for d in datas])]).astype(np.uint64)
+    comp, doff = ctx.deflate_streams(src, off)
+    for i, d in enumerate(datas):
+        got = comp[int(doff[i]): int(doff[i + 1])].tobytes()
+        assert got == oracle.deflate(d), (i, i % 7, len(d))
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, doff, off)
+    assert (st == 0).all() and np.array_equal(out, src)
+    assert np.array_equal(cons, np.diff(doff))

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import BLK_DYNAMIC, BLK_HUFF, ROOT, Corpus, HostModel, Oracle
+from helpers import BLK_DYNAMIC, BLK_HUFF, ROOT, Corpus, HostModel, Oracle, fuzz_streams
 
 
 @pytest.fixture(scope="module")
@@ -153,3 +153,13 @@ def test_build_block_matches_oracle(hm, oracle, corpus):
             got = np.unpackbits(hdr.view(np.uint8), bitorder="little")[:hdr_nbits]
             want = np.unpackbits(np.frombuffer(comp, np.uint8), bitorder="little")[:hdr_nbits]
             assert np.array_equal(got, want), (klass, n)
+
+
+def test_batched_parse_model_fuzz(hm, oracle):
+    """Structured random inputs (tests/helpers.py: fuzz_streams) through the lane-by-lane emulation of parse.cu."""
+    rng = np.random.default_rng(7)
+    for i, d in enumerate(fuzz_streams(rng, 140)):
+        _, wtok, wntok, _, _ = oracle.deflate_ex(d)
+        toks, ntok = hm.parse_stream(d, v2=True)
+        assert list(ntok) == list(wntok), (i, len(d))
+        assert np.array_equal(toks, wtok), (i, len(d))
