@@ -164,40 +164,58 @@ __device__ __forceinline__ void pm_merge_level(HuffScratch &S, int k, int n, int
 FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, uint8_t *len, uint16_t *code,
                                 HuffScratch &S)
 {
-  const int P = nsym > 32 ? kSortPad : 32;
-  int nz = 0, first = nsym;
-  FB_PFOR(i, P) {
-    const uint32_t f = i < nsym ? freq[i] : 0u;
-    S.keys[i] = f ? ((f << 9) | (uint32_t)i) : 0xffffffffu;
-    if (f) { nz++; if (i < first) first = i; }
-    if (i < nsym) { len[i] = 0; code[i] = 0; }
+  // gather the used symbols (any order: the sort below orders them), pad to a power of two
+  int first = nsym, n = 0;
+#if defined(__CUDA_ARCH__)
+  {
+    const int lane = FB_LANE;
+    const unsigned ltm = (1u << lane) - 1u;
+    for (int base = 0; base < nsym; base += 32) {
+      const int i = base + lane;
+      const uint32_t f = i < nsym ? freq[i] : 0u;
+      if (i < nsym) { len[i] = 0; code[i] = 0; }
+      const unsigned m = __ballot_sync(0xffffffffu, f != 0);
+      if (f) {
+        S.keys[n + __popc(m & ltm)] = (f << 9) | (uint32_t)i;
+        if (i < first) first = i;
+      }
+      n += __popc(m);
+    }
+    first = wmin(first);
   }
-  const int n = wsum(nz);
-  first = wmin(first);
+#else
+  for (int i = 0; i < nsym; i++) {
+    len[i] = 0; code[i] = 0;
+    if (freq[i]) { if (i < first) first = i; S.keys[n++] = (freq[i] << 9) | (uint32_t)i; }
+  }
+#endif
+  int P = 32;
+  while (P < n) P <<= 1;
+  FB_PFOR(i, P - n) S.keys[n + i] = 0xffffffffu;
   FB_WSYNC();
   if (n <= 2) { // :326-336: codes 0, 1 in literal order, length 1
     FB_PFOR(i, nsym) if (freq[i]) { len[i] = 1; code[i] = (uint16_t)(i != first); }
     FB_WSYNC();
     return;
   }
-  // sort ascending (any correct sort: keys are distinct) -- bitonic network
+  // sort ascending (any correct sort: keys are distinct) -- bitonic network over P >= n entries
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
 #if defined(__CUDA_ARCH__)
-      if (P == kSortPad) { // 8 independent compare-exchanges per lane and stage
+      if (P >= 256) { // several independent compare-exchanges per lane and stage
         uint32_t a[8], b[8];
         int ia[8];
+        const int nq = P >> 6;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const int t = FB_LANE + 32 * q;
           ia[q] = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-          a[q] = S.keys[ia[q]];
-          b[q] = S.keys[ia[q] | j];
+          if (q < nq) { a[q] = S.keys[ia[q]]; b[q] = S.keys[ia[q] | j]; }
         }
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const bool up = (ia[q] & k) == 0;
-          if ((a[q] > b[q]) == up) { S.keys[ia[q]] = b[q]; S.keys[ia[q] | j] = a[q]; }
+          if (q < nq && (a[q] > b[q]) == up) { S.keys[ia[q]] = b[q]; S.keys[ia[q] | j] = a[q]; }
         }
       } else
 #endif
@@ -224,6 +242,8 @@ FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, ui
     FB_WSYNC();
 #if defined(__CUDA_ARCH__)
     if (n <= 32) pm_merge_level<1, 32>(S, k, n, np, cap, cur);
+    else if (n <= 64) pm_merge_level<2, 64>(S, k, n, np, cap, cur);
+    else if (n <= 128) pm_merge_level<4, 128>(S, k, n, np, cap, cur);
     else pm_merge_level<9, 256>(S, k, n, np, cap, cur);
 #else
     FB_PFOR(i, n) { // leaf i sits after every pair of weight <= its own
