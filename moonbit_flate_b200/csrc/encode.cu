@@ -97,8 +97,12 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(DeflateJob j)
 {
   extern __shared__ __align__(16) uint8_t build_smem[];
   HuffScratch &S = reinterpret_cast<HuffScratch *>(build_smem)[threadIdx.x >> 5];
-  const uint64_t nwarps = (uint64_t)gridDim.x * kBuildWarps;
-  for (uint64_t blk = (uint64_t)blockIdx.x * kBuildWarps + (threadIdx.x >> 5); blk < j.nblocks; blk += nwarps) {
+  for (;;) { // blocks differ a lot in cost (alphabet size): hand them out one at a time
+    uint32_t b32 = 0;
+    if ((threadIdx.x & 31) == 0) b32 = atomicAdd(&j.counters[10], 1u);
+    b32 = __shfl_sync(kFull, b32, 0);
+    if (b32 >= j.nblocks) break;
+    const uint64_t blk = b32;
     const int kind = j.blk_kind[blk];
     if (kind == kKindStored) continue;
     const BlockRef r = block_ref(j, blk);
