@@ -701,13 +701,15 @@ void launch_inflate3(const InflateJob &j, int num_sms, cudaStream_t st)
   static int minb = 0;
   if (!minb) {
     const char *e = getenv("FB200_INFLATE_CTAS");
-    minb = e ? atoi(e) : 8;
-    if (minb != 6 && minb != 8 && minb != 12) minb = 8;
+    minb = e ? atoi(e) : 6; // 24 warps per SM at 80 registers: more occupancy only buys spills
+    if (minb != 4 && minb != 5 && minb != 6 && minb != 8 && minb != 12) minb = 6;
   }
   const uint64_t want = (j.nstreams + par::kWarps - 1) / par::kWarps;
   const uint64_t maxg = (uint64_t)num_sms * minb;
   const unsigned g = (unsigned)(want < maxg ? want : maxg);
-  if (minb == 6) par::k_inflate_par<6><<<g, par::kWarps * 32, 0, st>>>(j);
+  if (minb == 4) par::k_inflate_par<4><<<g, par::kWarps * 32, 0, st>>>(j);
+  else if (minb == 5) par::k_inflate_par<5><<<g, par::kWarps * 32, 0, st>>>(j);
+  else if (minb == 6) par::k_inflate_par<6><<<g, par::kWarps * 32, 0, st>>>(j);
   else if (minb == 8) par::k_inflate_par<8><<<g, par::kWarps * 32, 0, st>>>(j);
   else par::k_inflate_par<12><<<g, par::kWarps * 32, 0, st>>>(j);
 }
@@ -715,6 +717,8 @@ void launch_inflate3(const InflateJob &j, int num_sms, cudaStream_t st)
 void preload_inflate3_kernels()
 {
   cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, par::k_inflate_par<4>);
+  cudaFuncGetAttributes(&a, par::k_inflate_par<5>);
   cudaFuncGetAttributes(&a, par::k_inflate_par<6>);
   cudaFuncGetAttributes(&a, par::k_inflate_par<8>);
   cudaFuncGetAttributes(&a, par::k_inflate_par<12>);
