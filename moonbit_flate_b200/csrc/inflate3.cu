@@ -40,7 +40,7 @@ constexpr int kWarps = 4;
 constexpr uint32_t kLitLim = 256u << 4; // table entry = (symbol << 4) | code length
 constexpr uint32_t P_OK = 0, P_EOB = 1, P_BAD = 2;
 constexpr uint32_t kMinRange = 256;     // bits per lane at least
-constexpr int kLaneCopyMax = 24;
+constexpr int kLaneCopyMax = 16;
 constexpr uint32_t kPrefetchWords = 24;  // lane read-ahead: three 32-byte sectors
 constexpr uint32_t kSyncBits = 1536;   // round-0 run-in of a lane (bits)
 
