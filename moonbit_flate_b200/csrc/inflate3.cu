@@ -215,6 +215,10 @@ struct LBits {
   __device__ __forceinline__ uint32_t abit() const { return (wi << 5) + (uint32_t)bo; }
 };
 
+#ifdef FB_INFLATE_STEPSTAT
+__device__ unsigned long long g_stepstat[2];
+#endif
+
 // shared-memory loads by 32-bit shared address (the tables are reached through a reference, which would
 // otherwise cost a generic-to-shared conversion per access)
 __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
@@ -255,7 +259,13 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
   uint32_t flag = P_OK, cnt_out = 0, cnt_rec = 0;
   uint8_t *op = out + obase;
   bool act = run && start < e;
+#ifdef FB_INFLATE_STEPSTAT
+  uint32_t my_steps = 0, warp_steps = 0;
+#endif
   while (__any_sync(kFull, act)) {
+#ifdef FB_INFLATE_STEPSTAT
+    my_steps += act; warp_steps++;
+#endif
     const uint32_t bits = lb.peek();
     uint32_t e0 = lds_u16(lit_sa + ((bits & ((1u << kLB) - 1u)) << 1));
     if (__any_sync(kFull, act && e0 == 0)) {
@@ -325,6 +335,12 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
       else if (ab >= e_abs) act = false;
     }
   }
+#ifdef FB_INFLATE_STEPSTAT
+  if (WRITE) {
+    const uint32_t tot = __reduce_add_sync(kFull, my_steps);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&g_stepstat[0], (unsigned long long)warp_steps * 32ull); atomicAdd(&g_stepstat[1], (unsigned long long)tot); }
+  }
+#endif
   p_out = (run && start < e) ? lb.abit() - lead_bits : start;
   flag_out = flag;
   n_out = cnt_out;
@@ -713,6 +729,13 @@ void launch_inflate3(const InflateJob &j, int num_sms, cudaStream_t st)
   else if (minb == 8) par::k_inflate_par<8><<<g, par::kWarps * 32, 0, st>>>(j);
   else par::k_inflate_par<12><<<g, par::kWarps * 32, 0, st>>>(j);
 }
+
+#ifdef FB_INFLATE_STEPSTAT
+extern "C" void fb200_debug_stepstat(unsigned long long *out)
+{
+  cudaMemcpyFromSymbol(out, par::g_stepstat, 16);
+}
+#endif
 
 void preload_inflate3_kernels()
 {
