@@ -174,7 +174,26 @@ def cpu_baseline(src: np.ndarray, nseg_total: int, budget_s: float = 12.0):
 
 # ---------------------------------------------------------------------------
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, nvidia-smi helpers, ...) may write to fd 1; the contract is ONE JSON
+    line on stdout.  Everything but that line is sent to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -229,7 +248,7 @@ def main():
                                            "reference cannot be compiled here)"},
                 "e2e": {"value": round(v, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -413,7 +432,7 @@ def main():
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(h_np, nseg)
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
