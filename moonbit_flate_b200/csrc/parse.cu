@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -55,6 +56,11 @@ constexpr unsigned kFull = 0xffffffffu;
 #define FB_GTAB_PREFETCH 0 // measured: no gain (19.8 vs 19.4 ms per GiB)
 #endif
 constexpr bool kGtabPrefetch = FB_GTAB_PREFETCH != 0;
+#ifndef FB_WIDE_BATCH
+#define FB_WIDE_BATCH 1
+#endif
+constexpr bool kWideBatch = FB_WIDE_BATCH != 0;
+constexpr int kWideScratch = 1024; // bytes (= entries) per global-table warp
 
 // match_len tail (deflate-fast.mbt:286-307): number of equal bytes of src[s2..] and src[t..], at most a,
 // given that the first `from` already matched.  32 bytes per step; long matches take four steps per
@@ -101,7 +107,7 @@ __device__ __forceinline__ void publish_block(const DeflateJob &j, uint64_t blk,
 }
 
 template <bool MULTI, typename T, bool GTAB>
-__device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table)
+__device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table, uint8_t *scratch, int wide)
 {
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1;
@@ -150,6 +156,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
       int s = 0, next_emit = 0;
       uint32_t ntok = 0;
       bool modeM = false;
+      uint8_t wide_tag = 0;
       int loop_p0 = 0, k0 = 0;
 
       for (;;) {
@@ -165,6 +172,128 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         // byte each lane already holds, the next probe lane is s' - base, lanes
         // skipped by a match are simply not inserted.  (Exactness argument and CPU
         // emulation: tests/hostmodel/hostmodel.cu, fbm_parse_stream_v2.)
+        // ---- wide fast path (global-table warps, single-block streams): 64 positions per batch ----
+        // Two positions per lane (A = base + lane, B = base + 32 + lane) share the two serial trips to
+        // memory a batch costs (table entries, then candidate bytes).  Same rules as the 32-position batch
+        // below; in addition (a) buckets shared between an A and a B position are detected through a small
+        // tagged scratch ("some A position of this batch wrote this slot": conservative), and (b) after a
+        // restart at lane cur the reference probes consecutive positions only up to lane cur + 33 (skip
+        // schedule d_k = k for k <= 32, deflate-fast.mbt:178-187), so hits are looked for in that range only.
+        if (GTAB && !MULTI && kWideBatch && wide && modeM && s + 63 <= s_limit) {
+          const int base = s - 1;
+          const int posA = base + lane, posB = base + 32 + lane;
+          const uint32_t cvA = ld32u(srcb + posA), cvB = ld32u(srcb + posB);
+          if (lane == 0 && posA + 320 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + posA + 320));
+          const uint32_t hA = hash4(cvA), hB = hash4(cvB);
+          T *slotA = table + hA, *slotB = table + hB;
+          const T oldA = *slotA, oldB = *slotB;
+          wide_tag = (uint8_t)(wide_tag == 255 ? 1 : wide_tag + 1);
+          scratch[hA & (kWideScratch - 1)] = wide_tag;
+          __syncwarp();
+          const unsigned confA = __ballot_sync(kFull, (__match_any_sync(kFull, hA) & lt_mask) != 0);
+          const bool crossB = scratch[hB & (kWideScratch - 1)] == wide_tag;
+          const unsigned peersB = __match_any_sync(kFull, hB); // (every lane must take part: no short-circuit)
+          const unsigned confB = __ballot_sync(kFull, crossB || (peersB & lt_mask) != 0);
+          const int candA = (int)oldA, candB = (int)oldB;
+          const bool okA = (uint32_t)(posA - candA - 1) < (uint32_t)kMaxMatchOffset && lane != 0;
+          const bool okB = (uint32_t)(posB - candB - 1) < (uint32_t)kMaxMatchOffset;
+          uint32_t a0, a1, a2, b0, b1, b2;
+          {
+            const uintptr_t ca = (uintptr_t)(srcb + (okA ? candA : posA));
+            const uintptr_t cb = (uintptr_t)(srcb + (okB ? candB : posB));
+            const uint32_t *qa = (const uint32_t *)(ca & ~(uintptr_t)3), *qb = (const uint32_t *)(cb & ~(uintptr_t)3);
+            const uint32_t sa = (uint32_t)(ca & 3) * 8, sb = (uint32_t)(cb & 3) * 8;
+            const uint32_t u0 = __ldg(qa), u1 = __ldg(qa + 1), u2 = __ldg(qa + 2), u3 = __ldg(qa + 3);
+            const uint32_t v0 = __ldg(qb), v1 = __ldg(qb + 1), v2 = __ldg(qb + 2), v3 = __ldg(qb + 3);
+            a0 = __funnelshift_r(u0, u1, sa); a1 = __funnelshift_r(u1, u2, sa); a2 = __funnelshift_r(u2, u3, sa);
+            b0 = __funnelshift_r(v0, v1, sb); b1 = __funnelshift_r(v1, v2, sb); b2 = __funnelshift_r(v2, v3, sb);
+          }
+          // own bytes +4 / +8: A lanes read on into the B positions, B lanes stop at the end of the batch
+          const uint32_t dA4 = __shfl_down_sync(kFull, cvA, 4), dA8 = __shfl_down_sync(kFull, cvA, 8);
+          const uint32_t rB4 = __shfl_sync(kFull, cvB, (lane + 4) & 31), rB8 = __shfl_sync(kFull, cvB, (lane + 8) & 31);
+          const uint32_t pA1 = lane < 28 ? dA4 : rB4, pA2 = lane < 24 ? dA8 : rB8;
+          const uint32_t pB1 = rB4, pB2 = rB8; // valid for lanes <= 27 / <= 23
+          const bool hitA = okA && a0 == cvA, hitB = okB && b0 == cvB;
+          const int availB = lane <= 23 ? 8 : (lane <= 27 ? 4 : 0);
+          int extlA, extlB = 0;
+          {
+            const uint32_t x1 = a1 ^ pA1, x2 = a2 ^ pA2;
+            const int e1 = x1 ? ((__ffs(x1) - 1) >> 3) : 4, e2 = x2 ? ((__ffs(x2) - 1) >> 3) : 4;
+            extlA = e1 < 4 ? e1 : 4 + e2;
+            const uint32_t y1 = b1 ^ pB1, y2 = b2 ^ pB2;
+            const int f1 = y1 ? ((__ffs(y1) - 1) >> 3) : 4, f2 = y2 ? ((__ffs(y2) - 1) >> 3) : 4;
+            if (availB >= 4) extlB = (f1 < 4 || availB == 4) ? f1 : 4 + f2;
+          }
+          const int W = confA ? __ffs(confA) - 1 : (confB ? 32 + __ffs(confB) - 1 : 64);
+          if (W >= 2) {
+            const unsigned long long wmask = W < 64 ? (1ull << W) - 1ull : ~0ull;
+            const unsigned long long hitm =
+                ((unsigned long long)__ballot_sync(kFull, hitA) | ((unsigned long long)__ballot_sync(kFull, hitB) << 32)) & wmask;
+            unsigned long long keep = 0, emit = 0;
+            int extA = extlA, extB = extlB;
+            const int packedA = (extlA << 1) | (extlA == 8 ? 1 : 0);
+            const int packedB = (extlB << 1) | (extlB == availB ? 1 : 0);
+            int cur = 1;
+            bool block_done = false;
+            for (;;) {
+              const unsigned long long below = (1ull << cur) - 1ull;
+              const int lim = W < cur + 34 ? W : cur + 34;
+              const unsigned long long lmask = lim < 64 ? (1ull << lim) - 1ull : ~0ull;
+              const unsigned long long hm = hitm & ~below & lmask;
+              if (hm == 0) { // no hit in the consecutive range: literals up to lim, probing continues there
+                keep |= lmask & ~(below >> 1);
+                emit |= lmask & ~below;
+                next_emit = base + lim;
+                modeM = false; loop_p0 = base + cur + 1; k0 = lim - 1 - cur;
+                break;
+              }
+              const int m = __ffsll((long long)hm) - 1;
+              const unsigned long long upto = (2ull << m) - 1ull;
+              keep |= upto & ~(below >> 1);
+              emit |= upto & ~below; // literals cur..m-1, match at m
+              const int packed = m < 32 ? __shfl_sync(kFull, packedA, m) : __shfl_sync(kFull, packedB, m - 32);
+              int ext = packed >> 1;
+              const int s2 = base + m + 4;
+              if (packed & 1) { // the speculative bytes all matched: keep comparing
+                const int t = (m < 32 ? __shfl_sync(kFull, candA, m) : __shfl_sync(kFull, candB, m - 32)) + 4;
+                int s1 = s2 + kMaxMatchLength - 4;
+                if (s1 > n) s1 = n;
+                ext = match_tail(srcb, s2, t, s1 - s2, ext, lane);
+                if (lane == (m & 31)) { if (m < 32) extA = ext; else extB = ext; }
+              }
+              s = s2 + ext;
+              next_emit = s;
+              if (s >= s_limit) { block_done = true; break; } // :236-238
+              const int ncur = s - base;
+              if (ncur >= W) break; // next batch starts at s (still post-match mode)
+              cur = ncur;
+            }
+            const unsigned emit_lo = (unsigned)emit, emit_hi = (unsigned)(emit >> 32);
+#ifdef FB_PARSE_DEBUG
+            if (ntok + __popc(emit_lo) + __popc(emit_hi) > (uint32_t)n || s > n || (okA && (candA < 0 || candA >= posA)) || (okB && (candB < 0 || candB >= posB)))
+              printf("WIDE BAD st=%u base=%d lane=%d W=%d ntok=%u n=%d s=%d emit=%llx hitm=%llx candA=%d candB=%d posA=%d\n", st32, base, lane, W, ntok, n, s, emit, hitm, candA, candB, posA);
+#endif
+            if ((emit_lo >> lane) & 1u) {
+              uint32_t t = cvA & 0xffu; // emit_literal (:273-279)
+              if ((hitm >> lane) & 1ull) // match_token(l + 4 - 3, s - t - 1) (:228-233)
+                t = kMatchType + ((uint32_t)(extA + 1) << kLengthShift) + (uint32_t)(posA - candA - 1);
+              __stcs(&tok[ntok + (uint32_t)__popc(emit_lo & lt_mask)], t);
+            }
+            if ((emit_hi >> lane) & 1u) {
+              uint32_t t = cvB & 0xffu;
+              if ((hitm >> (32 + lane)) & 1ull)
+                t = kMatchType + ((uint32_t)(extB + 1) << kLengthShift) + (uint32_t)(posB - candB - 1);
+              __stcs(&tok[ntok + (uint32_t)__popc(emit_lo) + (uint32_t)__popc(emit_hi & lt_mask)], t);
+            }
+            ntok += (uint32_t)(__popc(emit_lo) + __popc(emit_hi));
+            if ((keep >> lane) & 1ull) *slotA = (T)posA; // kept positions share no bucket
+            if ((keep >> (32 + lane)) & 1ull) *slotB = (T)posB;
+            __syncwarp();
+            if (block_done) break;
+            continue;
+          }
+          __syncwarp();
+        }
         if (modeM && s + 31 <= s_limit) {
           const int base = s - 1;
           const int pos = base + lane;
@@ -389,23 +518,28 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
 // (the kernel is latency bound and shared memory caps it at 7 tables per SM)
 // keep theirs in a global scratch area that stays L2 resident.
 template <bool MULTI>
-__global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *gtables)
+__global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *gtables, int wide)
 {
   using T = typename std::conditional<MULTI, uint32_t, uint16_t>::type;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   if (warp < smem_warps) {
-    parse_worker<MULTI, T, false>(j, counter, reinterpret_cast<T *>(smem_raw) + (size_t)warp * kTableSize);
+    parse_worker<MULTI, T, false>(j, counter, reinterpret_cast<T *>(smem_raw) + (size_t)warp * kTableSize, nullptr, 0);
   } else {
     const int gw = (int)(blockDim.x >> 5) - smem_warps;
     T *table = reinterpret_cast<T *>(gtables) + ((size_t)blockIdx.x * gw + (warp - smem_warps)) * kTableSize;
-    parse_worker<MULTI, T, true>(j, counter, table);
+    // per-warp bucket scratch of the 64-position batches, behind the shared-memory tables
+    uint8_t *scratch = smem_raw + (size_t)smem_warps * kTableSize * sizeof(T) + (size_t)(warp - smem_warps) * kWideScratch;
+    parse_worker<MULTI, T, true>(j, counter, table, scratch, wide);
   }
 }
 
 void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
 
-static int g_parse_occ_single = 0, g_parse_occ_multi = 0, g_parse_gwarps = 0;
+// FB200_PARSE_WIDE=1 enables the 64-position batches of the global-table warps.  Exact (the GPU parity and
+// fuzz tests pass with it), but measured slower than the 32-position batches (21.6 vs 20.0 ms per GiB at
+// 5 + 18 warps): sharing the two memory trips does not pay for the extra work per batch.  Off by default.
+static int g_parse_occ_single = 0, g_parse_occ_multi = 0, g_parse_gwarps = 0, g_parse_wide = 0;
 static void *g_parse_gtables = nullptr;
 
 void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
@@ -419,16 +553,17 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
     const char *g = getenv("FB200_PARSE_GWARPS");
     int gw = g ? atoi(g) : 18;
     if (gw < 0) gw = 0;
-    if (gw > 25) gw = 25;
+    if (gw > 32) gw = 32;
     if (w + gw == 0) w = 1;
+    if (const char *wd = getenv("FB200_PARSE_WIDE")) g_parse_wide = atoi(wd) != 0;
     g_parse_occ_single = w;
     g_parse_occ_multi = w > 3 ? 3 : w;
     g_parse_gwarps = gw;
     if (gw) cudaMalloc(&g_parse_gtables, (size_t)num_sms * gw * kTableSize * 4);
     cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         g_parse_occ_single * kTableSize * 2);
+                         g_parse_occ_single * kTableSize * 2 + gw * (g_parse_wide ? kWideScratch : 0));
     cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         g_parse_occ_multi * kTableSize * 4);
+                         g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0));
     // leave room in the shared-memory carve-out for the co-resident k_post CTAs (K2 + K3 beside the parse)
     const char *co = getenv("FB200_PARSE_CARVEOUT");
     const int pct = co ? atoi(co) : 0; // 0: driver default (smallest carve-out that fits: most L1, which the parse needs)
@@ -468,10 +603,10 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
     av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
   }
-  k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * 2, st>>>(
-      j, j.counters + 0, g_parse_occ_single, g_parse_gtables);
-  k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4, st>>>(
-      j, j.counters + 1, g_parse_occ_multi, g_parse_gtables);
+  k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * 2 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
+      j, j.counters + 0, g_parse_occ_single, g_parse_gtables, g_parse_wide);
+  k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
+      j, j.counters + 1, g_parse_occ_multi, g_parse_gtables, g_parse_wide);
   if (persist && gw) {
     cudaStreamAttrValue av{};
     av.accessPolicyWindow.num_bytes = 0;
