@@ -281,13 +281,25 @@ def main():
     d_out_len = torch.zeros(nseg, dtype=torch.int64, device=dev)
     d_status = torch.zeros(nseg, dtype=torch.int32, device=dev)
     d_err_off = torch.zeros(nseg, dtype=torch.int64, device=dev)
+    # frame assembly on GPU 0 (N > 1): CUDA IPC + copy-engine peer copies that run beside the inflate pass;
+    # NCCL send/recv if IPC is unavailable on this box
     frame = None
-    if world > 1 and rank == 0:
-        frame = torch.empty(mg.frame_header_bytes(nseg * world) + world * dst_cap, dtype=torch.uint8, device=dev)
+    peer = None
+    frame_cap = mg.frame_header_bytes(nseg * world) + world * dst_cap
+    if world > 1:
+        if os.environ.get("FB200_FRAME_TRANSPORT", "ipc") == "ipc":
+            peer = mg.PeerFrame(ctx, rank, world, frame_cap, dev)
+            if not peer.available:
+                peer = None
+        if peer is None and rank == 0:
+            frame = torch.empty(frame_cap, dtype=torch.uint8, device=dev)
+        config["frame_transport"] = ("cuda-ipc peer copies (copy engines over NVLink), overlapped with the inflate pass"
+                                     if peer else "nccl send/recv")
 
     stage_acc = {}
     launches = [0]
     clen_box = [0]
+    frame_len = [0]
 
     def step(record=True):
         clen = ctx.deflate_segments_dev(d_src.data_ptr(), nbytes, SEG, d_dst.data_ptr(), dst_cap, d_seg_off.data_ptr())
@@ -298,10 +310,15 @@ def main():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
         if world > 1:
             sizes = d_seg_off[1:] - d_seg_off[:-1]
-            mg.assemble_frame(d_dst, sizes, SEG, rank, world, frame)
-            torch.cuda.synchronize()
+            if peer:  # asynchronous: the copies run while this rank inflates (no device-wide sync here)
+                frame_len[0] = peer.put(d_dst, sizes, SEG)
+            else:
+                frame_len[0] = mg.assemble_frame(d_dst, sizes, SEG, rank, world, frame)
+                torch.cuda.synchronize()
         ctx.inflate_batch_dev(d_dst.data_ptr(), d_seg_off.data_ptr(), nseg, d_out.data_ptr(), d_out_off.data_ptr(),
                               d_out_len.data_ptr(), d_status.data_ptr(), d_err_off.data_ptr())
+        if peer:
+            peer.wait()  # every rank's payload is in GPU 0's frame before the step ends
         if record:
             launches[0] += int(ctx.last_stats().kernel_launches)
             stage_acc["inflate"] = stage_acc.get("inflate", 0.0) + ctx.last_stage_ms()["inflate"]
@@ -322,6 +339,18 @@ def main():
         for i in list(range(0, nseg, max(1, nseg // 24)))[:24]:
             got = d_dst[int(offs[i]): int(offs[i + 1])].cpu().numpy().tobytes()
             assert got == orc.deflate(h_np[i * SEG:(i + 1) * SEG].tobytes()), f"segment {i} differs from the oracle"
+
+    if world > 1 and rank == 0:  # the assembled frame: sample streams of every rank inflate to that rank's segments
+        import zlib
+        fr = peer.view if peer else frame
+        seg_size, nseg_f, sizes_f, hdr_f = mg.parse_frame(fr)
+        assert seg_size == SEG and nseg_f == nseg * world and hdr_f + int(sizes_f.sum()) == frame_len[0]
+        offs_f = np.concatenate([[0], np.cumsum(sizes_f.numpy())]) + hdr_f
+        for r in range(world):
+            for i in (r * nseg, r * nseg + nseg // 2, (r + 1) * nseg - 1):
+                comp_i = fr[int(offs_f[i]): int(offs_f[i + 1])].cpu().numpy().tobytes()
+                want = corpus.fill(1, SEG, seed=args.seed, first=i).tobytes()
+                assert zlib.decompress(comp_i, -15) == want, f"frame stream {i} (rank {r}) does not inflate to its segment"
 
     # timed region: events on the stream the kernels are launched on
     step(record=False)  # same load right before the timed region (also keeps the clocks up for the sampler)

@@ -122,6 +122,24 @@ int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_
  *   magic "FB2\0" u32 | seg_size u32 | nseg u64 | comp_size u32[nseg] | streams */
 #define FB200_FRAME_MAGIC 0x00324246u
 uint64_t fb200_frame_header_bytes(uint64_t nseg);
+/* Frame assembly over NVLink without a staging copy and without SM time: the
+ * assembling rank allocates the frame buffer on its GPU and exports it with
+ * CUDA IPC; every other rank of the box maps it and, once the all-gathered
+ * segment sizes have given it its payload offset, puts its compacted streams
+ * straight into the frame with an asynchronous peer copy (copy engines), which
+ * runs beside whatever the context's compute stream does next.  handle = the
+ * 64 opaque bytes of a cudaIpcMemHandle_t, to be sent to the peers by the
+ * caller (torch.distributed / MPI / a pipe). */
+#define FB200_IPC_HANDLE_BYTES 64
+int fb200_mg_frame_alloc(fb200_ctx *ctx, uint64_t bytes, void **d_frame, uint8_t *handle);
+int fb200_mg_frame_open(fb200_ctx *ctx, const uint8_t *handle, void **d_frame);
+/* owner != 0: the pointer came from fb200_mg_frame_alloc (freed); else from _open (unmapped). */
+int fb200_mg_frame_close(fb200_ctx *ctx, void *d_frame, int owner);
+/* Asynchronous copy of n bytes from d_payload (this context's GPU) to d_frame + offset
+ * (local or IPC-mapped), ordered after everything queued so far on the context stream. */
+int fb200_mg_put(fb200_ctx *ctx, void *d_frame, uint64_t offset, const void *d_payload, uint64_t n);
+/* Blocks until every fb200_mg_put of this context has landed. */
+int fb200_mg_wait(fb200_ctx *ctx);
 
 /* ------------------------------------------------------------------ */
 /* Streaming objects mirroring the reference API (host buffers).       */

@@ -76,6 +76,11 @@ ABI = {
     "fb200_inflate_batch_dev": (
         C.c_int, [C.c_void_p, _u8p, _u64p, C.c_uint64, _u8p, _u64p, _u64p, C.c_void_p, C.c_void_p, _u64p]),
     "fb200_frame_header_bytes": (C.c_uint64, [C.c_uint64]),
+    "fb200_mg_frame_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "fb200_mg_frame_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fb200_mg_frame_close": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fb200_mg_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "fb200_mg_wait": (C.c_int, [C.c_void_p]),
     "fb200_writer_new": (C.c_void_p, [C.c_void_p, SINK_FN, C.c_void_p]),
     "fb200_writer_new_dict": (C.c_void_p, [C.c_void_p, SINK_FN, C.c_void_p, _u8p, C.c_uint64]),
     "fb200_writer_write": (C.c_int64, [C.c_void_p, _u8p, C.c_uint64]),
@@ -236,6 +241,31 @@ class Context:
 
     def cuda_stream(self) -> int:
         return int(_lib.fb200_cuda_stream(self._h) or 0)
+
+    # ---------------- multi-GPU frame (CUDA IPC + peer copies) ----------------
+    IPC_HANDLE_BYTES = 64
+
+    def mg_frame_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte IPC handle) of a frame buffer on this context's GPU."""
+        p = C.c_void_p()
+        h = (C.c_uint8 * self.IPC_HANDLE_BYTES)()
+        self._check(_lib.fb200_mg_frame_alloc(self._h, nbytes, C.byref(p), h), "fb200_mg_frame_alloc")
+        return int(p.value), bytes(h)
+
+    def mg_frame_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        h = (C.c_uint8 * self.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        self._check(_lib.fb200_mg_frame_open(self._h, h, C.byref(p)), "fb200_mg_frame_open")
+        return int(p.value)
+
+    def mg_frame_close(self, d_frame: int, owner: bool):
+        self._check(_lib.fb200_mg_frame_close(self._h, d_frame, 1 if owner else 0), "fb200_mg_frame_close")
+
+    def mg_put(self, d_frame: int, offset: int, d_payload: int, n: int):
+        self._check(_lib.fb200_mg_put(self._h, d_frame, offset, d_payload, n), "fb200_mg_put")
+
+    def mg_wait(self):
+        self._check(_lib.fb200_mg_wait(self._h), "fb200_mg_wait")
 
     def last_blocks(self, nblocks: int, tok_cap: int):
         ntok = np.zeros(nblocks, np.uint32)

@@ -74,6 +74,8 @@ struct fb200_ctx {
   DevBuf group_done;
   static constexpr int kMaxChunks = 4096;
   cudaStream_t s_in = nullptr, s_out = nullptr, s_post = nullptr;
+  cudaStream_t s_xfer = nullptr; // fb200_mg_put: peer copies into the frame (copy engines, beside the kernels)
+  cudaEvent_t e_xfer = nullptr;
   cudaEvent_t e_setup = nullptr, e_post = nullptr;
   DevBuf queue;
   // FB200_POST_OVERLAP=1 runs K2 + K3 (k_post) beside the parse.  Measured: the co-resident CTAs need a larger
@@ -146,6 +148,8 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->s_post, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->s_xfer, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->e_xfer, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->e_setup, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->e_post, cudaEventDisableTiming);
   if (const char *e = getenv("FB200_POST_OVERLAP")) ctx->post_overlap = atoi(e) != 0;
@@ -200,6 +204,8 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
   ctx->group_done.release();
   ctx->queue.release();
   if (ctx->s_post) cudaStreamDestroy(ctx->s_post);
+  if (ctx->s_xfer) cudaStreamDestroy(ctx->s_xfer);
+  if (ctx->e_xfer) cudaEventDestroy(ctx->e_xfer);
   if (ctx->e_setup) cudaEventDestroy(ctx->e_setup);
   if (ctx->e_post) cudaEventDestroy(ctx->e_post);
   if (ctx->d_wm) cudaFree(ctx->d_wm);
@@ -235,6 +241,72 @@ extern "C" uint64_t fb200_deflate_bound(uint64_t n, uint64_t seg_size)
 }
 
 extern "C" uint64_t fb200_frame_header_bytes(uint64_t nseg) { return 16 + 4 * nseg; }
+
+// ------------------------------------------------------------------
+// multi-GPU frame assembly: the frame lives on the assembling GPU, peers map it through
+// CUDA IPC and put their payload into it with copy-engine peer copies over NVLink.
+static_assert(sizeof(cudaIpcMemHandle_t) == FB200_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int fb200_mg_frame_alloc(fb200_ctx *ctx, uint64_t bytes, void **d_frame, uint8_t *handle)
+{
+  if (!ctx || !d_frame || !handle || bytes == 0) return FB200_ERR_ARG;
+  *d_frame = nullptr;
+  CK(cudaSetDevice(ctx->device));
+  void *p = nullptr;
+  CK(cudaMalloc(&p, bytes)); // a plain allocation of its own: IPC exports whole allocations
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    ctx->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return FB200_ERR_CUDA;
+  }
+  memcpy(handle, &h, sizeof h);
+  *d_frame = p;
+  return FB200_OK;
+}
+
+extern "C" int fb200_mg_frame_open(fb200_ctx *ctx, const uint8_t *handle, void **d_frame)
+{
+  if (!ctx || !d_frame || !handle) return FB200_ERR_ARG;
+  *d_frame = nullptr;
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CK(cudaIpcOpenMemHandle(d_frame, h, cudaIpcMemLazyEnablePeerAccess));
+  return FB200_OK;
+}
+
+extern "C" int fb200_mg_frame_close(fb200_ctx *ctx, void *d_frame, int owner)
+{
+  if (!ctx) return FB200_ERR_ARG;
+  if (!d_frame) return FB200_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->s_xfer));
+  if (owner) CK(cudaFree(d_frame));
+  else CK(cudaIpcCloseMemHandle(d_frame));
+  return FB200_OK;
+}
+
+extern "C" int fb200_mg_put(fb200_ctx *ctx, void *d_frame, uint64_t offset, const void *d_payload, uint64_t n)
+{
+  if (!ctx || !d_frame || (!d_payload && n)) return FB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return FB200_OK;
+  CK(cudaEventRecord(ctx->e_xfer, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->s_xfer, ctx->e_xfer, 0));
+  CK(cudaMemcpyAsync(static_cast<uint8_t *>(d_frame) + offset, d_payload, n, cudaMemcpyDeviceToDevice, ctx->s_xfer));
+  return FB200_OK;
+}
+
+extern "C" int fb200_mg_wait(fb200_ctx *ctx)
+{
+  if (!ctx) return FB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->s_xfer));
+  return FB200_OK;
+}
 
 // ------------------------------------------------------------------
 // deflate core: phase A = everything up to the output layout (returns the

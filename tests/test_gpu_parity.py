@@ -328,3 +328,26 @@ def test_fuzz_deflate_inflate_against_oracle(ctx, oracle):
     out, olen, st, eo, cons = ctx.inflate_batch(comp, doff, off)
     assert (st == 0).all() and np.array_equal(out, src)
     assert np.array_equal(cons, np.diff(doff))
+
+
+def test_peer_frame_single_rank(ctx, corpus):
+    """Frame assembly through the IPC frame buffer (fb200_mg_*), world size 1: header, sizes and payload of the
+    frame equal the rank's streams; the IPC handle of the buffer can be exported."""
+    import torch
+    from moonbit_flate_b200 import multigpu as mg
+    nseg, seg = 64, 65536
+    src = corpus.fill(nseg, seg, seed=9)
+    comp, off = ctx.deflate_segments(src, seg)
+    dev = torch.device("cuda", 0)
+    payload = torch.from_numpy(comp.copy()).to(dev)
+    sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(dev)
+    pf = mg.PeerFrame(ctx, 0, 1, mg.frame_header_bytes(nseg) + comp.size + 64, dev)
+    assert pf.available
+    total = pf.put(payload, sizes, seg)
+    pf.wait()
+    torch.cuda.synchronize()
+    seg_size, n, sizes_f, hdr = mg.parse_frame(pf.view)
+    assert (seg_size, n, hdr, total) == (seg, nseg, mg.frame_header_bytes(nseg), hdr + comp.size)
+    assert np.array_equal(sizes_f.numpy(), np.diff(off).astype(np.int64))
+    assert np.array_equal(pf.view[hdr:total].cpu().numpy(), comp)
+    pf.close()
