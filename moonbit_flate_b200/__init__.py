@@ -20,7 +20,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflate_b200.so")
+# FB200_LIB selects another build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("FB200_LIB") or os.path.join(_HERE, "libflate_b200.so")
 
 OK = 0
 ERR_ARG, ERR_DST_TOO_SMALL, ERR_CUDA, ERR_CLOSED, ERR_NOMEM = -1, -2, -3, -4, -5

@@ -56,8 +56,16 @@ constexpr unsigned kFull = 0xffffffffu;
 #define FB_GTAB_PREFETCH 0 // measured: no gain (19.8 vs 19.4 ms per GiB)
 #endif
 constexpr bool kGtabPrefetch = FB_GTAB_PREFETCH != 0;
+// Look-ahead of the post-match batches: the buckets of the 32 positions after this batch are read now (the
+// value is not needed before the batch ends, so the trip is off the critical path) and, when the batch ends,
+// the candidate bytes those entries point at are prefetched; the next batch then finds both of its serial
+// trips (table entry, candidate bytes) in cache.  A stale entry only costs a useless prefetch.
+// 0 off, 1 bucket prefetch to L2 only, 2 bucket read + candidate prefetch to L2, 3 same with candidates to L1
+#ifndef FB_PF
+#define FB_PF 1
+#endif
 #ifndef FB_WIDE_BATCH
-#define FB_WIDE_BATCH 1
+#define FB_WIDE_BATCH 0 // compiled out by default: it costs 16 registers (= 4 warps per SM) and measured slower
 #endif
 constexpr bool kWideBatch = FB_WIDE_BATCH != 0;
 constexpr int kWideScratch = 1024; // bytes (= entries) per global-table warp
@@ -304,6 +312,17 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           T *slot = table + h;
           const T old = *slot;
           const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
+          T la_old = 0;
+          bool la_ok = false;
+          if (FB_PF && !MULTI && pos + 36 <= n) {
+            const uint32_t hn = hash4(ld32u(srcb + pos + 32));
+            if (FB_PF == 1) {
+              if (GTAB) asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hn));
+            } else {
+              la_old = table[hn];
+              la_ok = true;
+            }
+          }
           unsigned conf;
           if (GTAB) { // table in global memory: no dependent read-back, compare buckets across lanes instead
             conf = __ballot_sync(kFull, (__match_any_sync(kFull, h) & lt_mask) != 0);
@@ -410,6 +429,10 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
             ntok += (uint32_t)__popc(emit);
             if (!GTAB) __syncwarp();
             if ((keep >> lane) & 1u) *slot = mine; // kept lanes share no bucket
+            if (FB_PF >= 2 && la_ok && (uint32_t)(pos + 32 - (int)la_old - 1) < (uint32_t)kMaxMatchOffset) {
+              if (FB_PF == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(srcb + (int)la_old));
+              else asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + (int)la_old));
+            }
             __syncwarp();
             if (block_done) break;
             continue;
@@ -536,9 +559,10 @@ __global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *g
 
 void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
 
-// FB200_PARSE_WIDE=1 enables the 64-position batches of the global-table warps.  Exact (the GPU parity and
-// fuzz tests pass with it), but measured slower than the 32-position batches (21.6 vs 20.0 ms per GiB at
-// 5 + 18 warps): sharing the two memory trips does not pay for the extra work per batch.  Off by default.
+// FB200_PARSE_WIDE=1 (in a build with -DFB_WIDE_BATCH=1) enables the 64-position batches of the global-table
+// warps.  Exact (the GPU parity and fuzz tests pass with it), but measured slower than the 32-position batches
+// (21.6 vs 20.0 ms per GiB at 5 + 18 warps): sharing the two memory trips does not pay for the extra work per
+// batch.  Compiled out by default.
 static int g_parse_occ_single = 0, g_parse_occ_multi = 0, g_parse_gwarps = 0, g_parse_wide = 0;
 static void *g_parse_gtables = nullptr;
 
@@ -547,15 +571,16 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
   static bool inited = false;
   if (!inited) {
     const char *e = getenv("FB200_PARSE_WARPS");
-    int w = e ? atoi(e) : 6;
+    int w = e ? atoi(e) : 5;
     if (w < 0) w = 0;
     if (w > 7) w = 7;
     const char *g = getenv("FB200_PARSE_GWARPS");
-    int gw = g ? atoi(g) : 18;
+    int gw = g ? atoi(g) : 25;
     if (gw < 0) gw = 0;
     if (gw > 32) gw = 32;
     if (w + gw == 0) w = 1;
-    if (const char *wd = getenv("FB200_PARSE_WIDE")) g_parse_wide = atoi(wd) != 0;
+    if (w + gw > 32) gw = 32 - w; // one CTA per SM, at most 1024 threads
+    if (const char *wd = getenv("FB200_PARSE_WIDE")) g_parse_wide = kWideBatch && atoi(wd) != 0;
     g_parse_occ_single = w;
     g_parse_occ_multi = w > 3 ? 3 : w;
     g_parse_gwarps = gw;
@@ -579,7 +604,7 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
   static int persist = -1;
   if (persist < 0) {
     const char *e = getenv("FB200_PARSE_L2PERSIST");
-    persist = e ? atoi(e) : 1;
+    persist = e ? atoi(e) : 0;
     if (persist && gw) {
       int dev = 0, maxp = 0;
       cudaGetDevice(&dev);
