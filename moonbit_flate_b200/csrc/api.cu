@@ -76,11 +76,18 @@ struct fb200_ctx {
   cudaStream_t s_in = nullptr, s_out = nullptr, s_post = nullptr;
   cudaStream_t s_xfer = nullptr; // fb200_mg_put: peer copies into the frame (copy engines, beside the kernels)
   cudaEvent_t e_xfer = nullptr;
-  cudaEvent_t e_setup = nullptr, e_post = nullptr;
-  DevBuf queue;
-  // FB200_POST_OVERLAP=1 runs K2 + K3 (k_post) beside the parse.  Measured: the co-resident CTAs need a larger
-  // shared-memory carve-out (FB200_PARSE_CARVEOUT=77), and the L1 the parse loses costs as much as is hidden.
-  bool post_overlap = false;
+  cudaStream_t s_post2 = nullptr;
+  // Group pipeline of the host-buffer deflate (FB200_DEFLATE_PIPELINE, default on): after the parse, K2..K4 run
+  // group by group (two streams, so that K3 of one group overlaps K4 of the previous one) and the output of a
+  // packed group is copied back while the later groups are still being packed.
+  bool pipeline = true;
+  uint64_t group_bytes = 64ull << 20;
+  static constexpr int kMaxGroups = 256;
+  DevBuf d_group;                 // [kMaxGroups] u32: K3 work counters
+  DevBuf d_group_bounds;          // [kMaxGroups + 1] u64: first block of every group
+  uint64_t *h_gbounds = nullptr;  // pinned [kMaxGroups + 1] block bounds, [kMaxGroups + 1] output byte offsets
+  std::vector<cudaEvent_t> e_gsize, e_gdone, e_gchain;
+  cudaEvent_t e_bounds = nullptr, e_parsed = nullptr;
   cudaEvent_t e_in[2] = {}, e_comp[2] = {}, e_out[2] = {};
   uint64_t chunk_bytes = 32ull << 20;
   uint64_t *pinned = nullptr; // small pinned read-back area
@@ -136,7 +143,8 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   }
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost((void **)&ctx->pinned, 64 * sizeof(uint64_t)) != cudaSuccess) {
+      cudaMallocHost((void **)&ctx->pinned, 64 * sizeof(uint64_t)) != cudaSuccess ||
+      cudaMallocHost((void **)&ctx->h_gbounds, 2 * (fb200_ctx::kMaxGroups + 1) * sizeof(uint64_t)) != cudaSuccess) {
     delete ctx;
     cudaGetLastError();
     return FB200_ERR_CUDA;
@@ -150,9 +158,14 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   cudaStreamCreateWithFlags(&ctx->s_post, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->s_xfer, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->e_xfer, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&ctx->e_setup, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&ctx->e_post, cudaEventDisableTiming);
-  if (const char *e = getenv("FB200_POST_OVERLAP")) ctx->post_overlap = atoi(e) != 0;
+  cudaStreamCreateWithFlags(&ctx->s_post2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->e_bounds, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->e_parsed, cudaEventDisableTiming);
+  if (const char *e = getenv("FB200_DEFLATE_PIPELINE")) ctx->pipeline = atoi(e) != 0;
+  if (const char *e = getenv("FB200_GROUP_MB")) {
+    const long mb = atol(e);
+    if (mb > 0) ctx->group_bytes = (uint64_t)mb << 20;
+  }
   for (int i = 0; i < 2; i++) {
     cudaEventCreateWithFlags(&ctx->e_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->e_comp[i], cudaEventDisableTiming);
@@ -202,12 +215,17 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
     if (ctx->e_out[i]) cudaEventDestroy(ctx->e_out[i]);
   }
   ctx->group_done.release();
-  ctx->queue.release();
+  ctx->d_group.release();
+  ctx->d_group_bounds.release();
+  for (auto *v : {&ctx->e_gsize, &ctx->e_gdone, &ctx->e_gchain})
+    for (cudaEvent_t e : *v) cudaEventDestroy(e);
+  if (ctx->e_bounds) cudaEventDestroy(ctx->e_bounds);
+  if (ctx->e_parsed) cudaEventDestroy(ctx->e_parsed);
+  if (ctx->h_gbounds) cudaFreeHost(ctx->h_gbounds);
   if (ctx->s_post) cudaStreamDestroy(ctx->s_post);
+  if (ctx->s_post2) cudaStreamDestroy(ctx->s_post2);
   if (ctx->s_xfer) cudaStreamDestroy(ctx->s_xfer);
   if (ctx->e_xfer) cudaEventDestroy(ctx->e_xfer);
-  if (ctx->e_setup) cudaEventDestroy(ctx->e_setup);
-  if (ctx->e_post) cudaEventDestroy(ctx->e_post);
   if (ctx->d_wm) cudaFree(ctx->d_wm);
   if (ctx->wm_vals) cudaFreeHost(ctx->wm_vals);
   if (ctx->h_flags) cudaFreeHost((void *)ctx->h_flags);
@@ -309,46 +327,95 @@ extern "C" int fb200_mg_wait(fb200_ctx *ctx)
 }
 
 // ------------------------------------------------------------------
-// deflate core: phase A = everything up to the output layout (returns the
-// total compressed size), phase B = bit packing into d_dst.
+// deflate core.  One launch of the parse over the whole batch, then K2, K3, layout and K4.  Device-buffer calls
+// run them over the whole batch in stream order.  Host-buffer calls cut the streams into groups and run K2..K4
+// group by group on two streams; the output of a packed group travels back to the host (copy engine) while
+// the later groups are being packed.  (Running K2..K4 of finished groups beside the still running parse was
+// built and measured: the parse leaves ~12 K registers and 3 KB of shared memory per SM, the co-resident CTAs
+// crawl -- group 0's histogram + codes took 12 ms -- and making room for them, a 196 KB carve-out, costs the
+// parse 1.1 ms of L1 hits.  The SMs have no idle capacity to give; the copy engines do.)
 
-// nb_known: number of blocks if the caller knows it (host-side offsets), ~0 to read it back from the device.
-// avail: arrival watermark for host-buffer calls (see DeflateJob::avail), or null.
-static int deflate_phase_a_launch(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t *d_src_off, uint64_t ns,
-                                  uint64_t n_total, uint64_t *d_dst_off, uint64_t nb_known, const uint32_t *avail)
+struct DeflateIo {
+  const uint8_t *d_src = nullptr;
+  const uint64_t *d_src_off = nullptr; // device [ns + 1]
+  uint64_t ns = 0, n_total = 0;
+  uint64_t *d_dst_off = nullptr;       // device [ns + 1]
+  uint64_t nb_known = ~0ull;           // number of blocks if the caller knows it, else read back
+  const uint32_t *avail = nullptr;     // arrival watermark (host-buffer calls)
+  uint8_t *d_dst = nullptr;            // device output (4-byte aligned)
+  uint64_t d_cap = 0;                  // its capacity in bytes
+  uint8_t *h_dst = nullptr;            // host-buffer calls: where finished groups are copied to
+  uint64_t h_cap = 0;
+};
+
+template <typename Feed>
+static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t *total_out)
 {
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  const uint64_t ns = io.ns;
   ctx->stats = fb200_stats{};
+  *total_out = 0;
   if (ns > 0xfffffff0ull) { ctx->err = "too many streams"; return FB200_ERR_ARG; }
+  if ((reinterpret_cast<uintptr_t>(io.d_dst) & 3) != 0) { ctx->err = "device dst must be 4-byte aligned"; return FB200_ERR_ARG; }
   DeflateJob &j = ctx->last;
   j = DeflateJob{};
-  j.src = d_src;
-  j.stream_off = d_src_off;
+  j.src = io.d_src;
+  j.stream_off = io.d_src_off;
   j.nstreams = ns;
   CK(ctx->stream_blk0.ensure((ns + 1) * 8));
   CK(ctx->stream_bytes.ensure((ns + 1) * 8));
   CK(ctx->stream_trailer.ensure((ns + 1) * 8));
   CK(ctx->counters.ensure(64));
+  CK(ctx->d_group.ensure(fb200_ctx::kMaxGroups * 4));
+  CK(ctx->d_group_bounds.ensure((fb200_ctx::kMaxGroups + 1) * 8));
   j.stream_blk0 = ctx->stream_blk0.as<uint64_t>();
   j.stream_bytes = ctx->stream_bytes.as<uint64_t>();
   j.stream_trailer_bit = ctx->stream_trailer.as<uint64_t>();
-  j.dst_off = d_dst_off;
+  j.dst_off = io.d_dst_off;
   j.counters = ctx->counters.as<uint32_t>();
-  j.avail = avail;
+  j.avail = io.avail;
+  j.dst = io.d_dst;
+  j.dst_cap = io.d_cap & ~3ull; // K4 clears and writes whole words
   CK(cudaMemsetAsync(j.counters, 0, 64, st));
   uint64_t launches = 0;
   for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
 
+  // groups: ~group_bytes of input each
+  const bool piped = ctx->pipeline && ns > 0 && io.h_dst != nullptr;
+  uint64_t gs = ns ? ns : 1;
+  if (piped) {
+    const double avg = ns ? (double)io.n_total / (double)ns : 1.0;
+    gs = (uint64_t)((double)ctx->group_bytes / (avg > 1.0 ? avg : 1.0));
+    if (gs == 0) gs = 1;
+    if (gs > ns) gs = ns;
+    if ((ns + gs - 1) / gs > (uint64_t)fb200_ctx::kMaxGroups) gs = (ns + fb200_ctx::kMaxGroups - 1) / fb200_ctx::kMaxGroups;
+  }
+  const uint64_t ngroups = ns ? (ns + gs - 1) / gs : 0;
+  uint32_t *d_k3cnt = ctx->d_group.as<uint32_t>();
+  CK(cudaMemsetAsync(d_k3cnt, 0, fb200_ctx::kMaxGroups * 4, st));
+  while (ctx->e_gsize.size() < ngroups) {
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); // (timed: FB200_TRACE prints the group timeline)
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    ctx->e_gsize.push_back(e0);
+    ctx->e_gdone.push_back(e1);
+    ctx->e_gchain.push_back(e2);
+  }
+  uint64_t *h_bb = ctx->h_gbounds, *h_goff = ctx->h_gbounds + fb200_ctx::kMaxGroups + 1;
+
   ctx->stage_begin(FB200_STAGE_SETUP);
   launch_count_blocks(j, st);
   launch_scan_u64(j.stream_blk0, j.stream_blk0, ns, st);
-  launches += 2;
-  uint64_t nb = nb_known;
+  launch_gather_u64(ctx->d_group_bounds.as<uint64_t>(), j.stream_blk0, gs, ns, ngroups + 1, st);
+  CK(cudaMemcpyAsync(h_bb, ctx->d_group_bounds.p, (ngroups + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->e_bounds, st));
+  launches += 3;
+  uint64_t nb = io.nb_known;
   if (nb == ~0ull) {
-    CK(cudaMemcpyAsync(ctx->pinned, j.stream_blk0 + ns, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    nb = ctx->pinned[0];
+    nb = h_bb[ngroups];
   }
   if (nb > 0x7fffffffull) { ctx->err = "too many blocks in one call"; return FB200_ERR_ARG; }
   j.nblocks = nb;
@@ -362,7 +429,7 @@ static int deflate_phase_a_launch(fb200_ctx *ctx, const uint8_t *d_src, const ui
   CK(ctx->blk_hdr.ensure(nbp * kHdrWords * 4));
   CK(ctx->blk_freq.ensure(nbp * kFreqStride * 4));
   CK(ctx->blk_code.ensure(nbp * kFreqStride * 4));
-  CK(ctx->tokens.ensure((n_total + 16) * 4));
+  CK(ctx->tokens.ensure((io.n_total + 16) * 4));
   j.blk_stream = ctx->blk_stream.as<uint32_t>();
   j.blk_ntok = ctx->blk_ntok.as<uint32_t>();
   j.blk_kind = ctx->blk_kind.as<uint8_t>();
@@ -373,81 +440,116 @@ static int deflate_phase_a_launch(fb200_ctx *ctx, const uint8_t *d_src, const ui
   j.blk_freq = ctx->blk_freq.as<uint32_t>();
   j.blk_code = ctx->blk_code.as<uint32_t>();
   j.tokens = ctx->tokens.as<uint32_t>();
-  ctx->last_n_total = n_total;
+  ctx->last_n_total = io.n_total;
   CK(cudaMemsetAsync(j.blk_ntok, 0, nbp * 4, st));
   CK(cudaMemsetAsync(j.blk_bits, 0, nbp * 4, st));
-
   launch_fill_blocks(j, st);
-  if (ctx->post_overlap) {
-    CK(ctx->queue.ensure(nbp * 4));
-    j.queue = ctx->queue.as<uint32_t>();
-    CK(cudaMemsetAsync(j.queue, 0, nbp * 4, st));
-  }
+  launches += 1;
   ctx->stage_end(FB200_STAGE_SETUP);
-  if (ctx->post_overlap) { // K2 + K3 run beside the parse, block by block as the parse finishes them
-    CK(cudaEventRecord(ctx->e_setup, st));
-    CK(cudaStreamWaitEvent(ctx->s_post, ctx->e_setup, 0));
-  }
+
   ctx->stage_begin(FB200_STAGE_PARSE);
   launch_parse(j, ctx->num_sms, st);
   ctx->stage_end(FB200_STAGE_PARSE);
-  if (ctx->post_overlap) {
-    launch_post(j, ctx->num_sms, ctx->s_post);
-    CK(cudaEventRecord(ctx->e_post, ctx->s_post));
-    ctx->stage_begin(FB200_STAGE_BUILD); // = what the code construction still costs after the parse has ended
-    CK(cudaStreamWaitEvent(st, ctx->e_post, 0));
-    ctx->stage_end(FB200_STAGE_BUILD);
-  } else {
-    ctx->stage_begin(FB200_STAGE_HISTOGRAM);
-    launch_histogram(j, st);
-    ctx->stage_end(FB200_STAGE_HISTOGRAM);
-    ctx->stage_begin(FB200_STAGE_BUILD);
-    launch_build_codes(j, ctx->num_sms, st);
-    ctx->stage_end(FB200_STAGE_BUILD);
+  launches += 2;
+  CK(cudaGetLastError());
+  {
+    const int rc = feed(); // host-buffer calls: queue the H2D chunks + watermark updates
+    if (rc != FB200_OK) return rc;
   }
-  ctx->stage_begin(FB200_STAGE_LAYOUT);
-  launch_layout(j, st);
-  launch_scan_u64(j.stream_bytes, j.dst_off, ns, st);
-  ctx->stage_end(FB200_STAGE_LAYOUT);
-  launches += 7;
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(ctx->pinned, j.dst_off + ns, 8, cudaMemcpyDeviceToHost, st));
-  ctx->stats.nblocks = nb;
-  ctx->stats.kernel_launches = launches;
-  return FB200_OK;
-}
 
-static int deflate_phase_a_finish(fb200_ctx *ctx, uint64_t *total_out)
-{
-  CK(cudaStreamSynchronize(ctx->stream));
-  *total_out = ctx->pinned[0];
-  return FB200_OK;
-}
+  // K2 .. K4 of one group on stream sp
+  auto launch_group = [&](uint64_t g, cudaStream_t sp, bool chain) -> int {
+    DeflateJob jg = j;
+    jg.st_begin = g * gs;
+    jg.st_end = jg.st_begin + gs < ns ? jg.st_begin + gs : ns;
+    jg.blk_begin = piped ? h_bb[g] : 0;
+    jg.blk_end = piped ? h_bb[g + 1] : nb;
+    jg.work_counter = d_k3cnt + g;
+    if (!piped) ctx->stage_begin(FB200_STAGE_HISTOGRAM);
+    launch_histogram(jg, sp);
+    if (!piped) { ctx->stage_end(FB200_STAGE_HISTOGRAM); ctx->stage_begin(FB200_STAGE_BUILD); }
+    launch_build_codes(jg, ctx->num_sms, sp);
+    if (!piped) { ctx->stage_end(FB200_STAGE_BUILD); ctx->stage_begin(FB200_STAGE_LAYOUT); }
+    if (chain && g > 0) CK(cudaStreamWaitEvent(sp, ctx->e_gchain[g - 1], 0)); // offsets + shared edge word of the previous group
+    launch_layout(jg, sp);
+    launch_scan_u64(j.stream_bytes + jg.st_begin, j.dst_off + jg.st_begin, jg.st_end - jg.st_begin, sp,
+                    g ? j.dst_off + jg.st_begin : nullptr, h_goff + g + 1);
+    CK(cudaEventRecord(ctx->e_gsize[g], sp));
+    if (!piped) { ctx->stage_end(FB200_STAGE_LAYOUT); ctx->stage_begin(FB200_STAGE_PACK); }
+    launch_zero_range(jg, sp);
+    if (chain) CK(cudaEventRecord(ctx->e_gchain[g], sp));
+    launch_pack(jg, sp);
+    if (!piped) ctx->stage_end(FB200_STAGE_PACK);
+    CK(cudaEventRecord(ctx->e_gdone[g], sp));
+    launches += 7;
+    CK(cudaGetLastError());
+    return FB200_OK;
+  };
+  // output of group g back to the host (host-buffer calls)
+  h_goff[0] = 0;
+  bool overflow = false;
+  auto copy_group = [&](uint64_t g) -> int {
+    const uint64_t a = h_goff[g], b = h_goff[g + 1];
+    if (b > io.h_cap || b > j.dst_cap) { overflow = true; return FB200_OK; }
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->e_gdone[g], 0));
+    if (b > a) CK(cudaMemcpyAsync(io.h_dst + a, io.d_dst + a, b - a, cudaMemcpyDeviceToHost, ctx->s_out));
+    return FB200_OK;
+  };
 
-static int deflate_phase_a(fb200_ctx *ctx, const uint8_t *d_src, const uint64_t *d_src_off, uint64_t ns,
-                           uint64_t n_total, uint64_t *d_dst_off, uint64_t *total_out)
-{
-  int rc = deflate_phase_a_launch(ctx, d_src, d_src_off, ns, n_total, d_dst_off, ~0ull, nullptr);
-  if (rc != FB200_OK) return rc;
-  return deflate_phase_a_finish(ctx, total_out);
-}
-
-static int deflate_phase_b(fb200_ctx *ctx, uint8_t *d_dst, uint64_t total)
-{
-  cudaStream_t st = ctx->stream;
-  DeflateJob &j = ctx->last;
-  if ((reinterpret_cast<uintptr_t>(d_dst) & 3) != 0) { ctx->err = "device dst must be 4-byte aligned"; return FB200_ERR_ARG; }
-  j.dst = d_dst;
-  ctx->stage_begin(FB200_STAGE_PACK);
-  CK(cudaMemsetAsync(d_dst, 0, (total + 3) & ~3ull, st));
-  launch_pack(j, st);
-  ctx->stage_end(FB200_STAGE_PACK);
-  ctx->stats.kernel_launches += 2;
-  CK(cudaGetLastError());
+  if (!piped) {
+    if (ngroups) {
+      const int rc = launch_group(0, st, false);
+      if (rc != FB200_OK) return rc;
+      CK(cudaStreamSynchronize(st));
+      if (io.h_dst) {
+        const int rc2 = copy_group(0);
+        if (rc2 != FB200_OK) return rc2;
+      }
+    }
+  } else {
+    CK(cudaEventRecord(ctx->e_parsed, st));
+    CK(cudaStreamWaitEvent(ctx->s_post, ctx->e_parsed, 0));
+    CK(cudaStreamWaitEvent(ctx->s_post2, ctx->e_parsed, 0));
+    CK(cudaEventSynchronize(ctx->e_bounds)); // block bounds of the groups are on the host (queued before the parse)
+    for (uint64_t g = 0; g < ngroups; g++) {
+      const int rc = launch_group(g, (g & 1) ? ctx->s_post2 : ctx->s_post, true);
+      if (rc != FB200_OK) return rc;
+    }
+    for (uint64_t g = 0; g < ngroups; g++) {
+      CK(cudaEventSynchronize(ctx->e_gsize[g]));
+      const int rc = copy_group(g);
+      if (rc != FB200_OK) return rc;
+    }
+    // "pack" stage of the pipeline = K2 .. K4 of all groups
+    CK(cudaEventRecord(ctx->ev0[FB200_STAGE_PACK], st)); // = end of the parse (stream order)
+    CK(cudaStreamSynchronize(ctx->s_post));
+    CK(cudaStreamSynchronize(ctx->s_post2));
+    CK(cudaEventRecord(ctx->ev1[FB200_STAGE_PACK], st));
+    ctx->ev_used[FB200_STAGE_PACK] = true;
+  }
   CK(cudaMemcpyAsync(ctx->pinned, j.counters, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const uint32_t *c = reinterpret_cast<const uint32_t *>(ctx->pinned);
-  if (c[4] != 0) {
+  if (io.h_dst) CK(cudaStreamSynchronize(ctx->s_out));
+  static const bool trace = getenv("FB200_TRACE") != nullptr;
+  if (trace && piped) {
+    float t_p0 = 0, t_p1 = 0;
+    cudaEventElapsedTime(&t_p0, ctx->ev0[FB200_STAGE_SETUP], ctx->ev0[FB200_STAGE_PARSE]);
+    cudaEventElapsedTime(&t_p1, ctx->ev0[FB200_STAGE_SETUP], ctx->ev1[FB200_STAGE_PARSE]);
+    fprintf(stderr, "[fb200] deflate: parse %.2f .. %.2f ms; groups (layout done / packed):", t_p0, t_p1);
+    for (uint64_t g = 0; g < ngroups; g++) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, ctx->ev0[FB200_STAGE_SETUP], ctx->e_gsize[g]);
+      cudaEventElapsedTime(&b, ctx->ev0[FB200_STAGE_SETUP], ctx->e_gdone[g]);
+      fprintf(stderr, " %.2f/%.2f", a, b);
+    }
+    fprintf(stderr, "\n");
+  }
+  const uint64_t total = ngroups ? h_goff[ngroups] : 0;
+  *total_out = total;
+  ctx->stats.nblocks = nb;
+  ctx->stats.kernel_launches = launches;
+  if (overflow || total > j.dst_cap || (io.h_dst && total > io.h_cap)) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
+  if (reinterpret_cast<const uint32_t *>(ctx->pinned)[4] != 0) {
     ctx->err = "internal error: packed block size differs from the computed layout";
     return FB200_ERR_CUDA;
   }
@@ -459,12 +561,18 @@ extern "C" int fb200_deflate_streams_dev(fb200_ctx *ctx, const uint8_t *d_src, c
                                          uint64_t *d_dst_off, uint64_t *out_len)
 {
   if (!ctx || !d_src_off || !d_dst_off || !out_len || (!d_src && n_total) || !d_dst) return FB200_ERR_ARG;
+  DeflateIo io;
+  io.d_src = d_src;
+  io.d_src_off = d_src_off;
+  io.ns = nstreams;
+  io.n_total = n_total;
+  io.d_dst_off = d_dst_off;
+  io.d_dst = d_dst;
+  io.d_cap = dst_cap;
   uint64_t total = 0;
-  int rc = deflate_phase_a(ctx, d_src, d_src_off, nstreams, n_total, d_dst_off, &total);
-  if (rc != FB200_OK) return rc;
+  const int rc = deflate_run(ctx, io, [] { return FB200_OK; }, &total);
   *out_len = total;
-  if (((total + 3) & ~3ull) > dst_cap) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
-  return deflate_phase_b(ctx, d_dst, total);
+  return rc;
 }
 
 extern "C" int fb200_deflate_segments_dev(fb200_ctx *ctx, const uint8_t *d_src, uint64_t n, uint64_t seg_size,
@@ -544,10 +652,24 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
   } else {
     launch_fill_seg_off(d_off, ns, seg_size, n, st);
   }
-  int rc = deflate_phase_a_launch(ctx, d_src, d_off, ns, n, ctx->p_off_out[0].as<uint64_t>(), nb, ctx->d_wm);
-  if (rc != FB200_OK) return rc;
-  // the kernels are queued; now feed them
-  {
+  // device output: the caller's capacity bounds it (a call that does not fit reports the need and writes nothing more)
+  uint64_t dcap = 2 * n + 640 * (nb + ns) + 16 * ns + 64;
+  if (dcap > ((dst_cap + 3) & ~3ull) + 4) dcap = ((dst_cap + 3) & ~3ull) + 4;
+  CK(ctx->p_out[0].ensure(dcap + 16));
+  DeflateIo io;
+  io.d_src = d_src;
+  io.d_src_off = d_off;
+  io.ns = ns;
+  io.n_total = n;
+  io.d_dst_off = ctx->p_off_out[0].as<uint64_t>();
+  io.nb_known = nb;
+  io.avail = ctx->d_wm;
+  io.d_dst = ctx->p_out[0].as<uint8_t>();
+  io.d_cap = dcap;
+  io.h_dst = dst;
+  io.h_cap = dst_cap;
+  // once the kernels are queued: feed them
+  auto feed = [&]() -> int {
     uint64_t done = 0;
     for (size_t c = 0; c < cuts.size(); c++) {
       uint64_t upto = c + 1 == cuts.size() ? n : ((cuts[c].bytes + 127) & ~127ull);
@@ -559,20 +681,19 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
       ctx->wm_vals[c] = (uint32_t)cuts[c].streams;
       CK(cudaMemcpyAsync(ctx->d_wm, &ctx->wm_vals[c], 4, cudaMemcpyHostToDevice, ctx->s_in));
     }
-  }
+    return FB200_OK;
+  };
   uint64_t total = 0;
-  rc = deflate_phase_a_finish(ctx, &total);
-  if (rc != FB200_OK) return rc;
+  const int rc = deflate_run(ctx, io, feed, &total);
   *out_len = total;
-  if (total > dst_cap) { ctx->err = "dst_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
-  CK(ctx->p_out[0].ensure(total + 16));
-  rc = deflate_phase_b(ctx, ctx->p_out[0].as<uint8_t>(), total);
-  if (rc != FB200_OK) return rc;
-  if (total) CK(cudaMemcpyAsync(dst, ctx->p_out[0].p, total, cudaMemcpyDeviceToHost, st));
+  if (rc != FB200_OK) {
+    cudaStreamSynchronize(ctx->s_in);
+    return rc;
+  }
   if (dst_off) CK(cudaMemcpyAsync(dst_off, ctx->p_off_out[0].p, (ns + 1) * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaStreamSynchronize(ctx->s_in));
-  ctx->stats.kernel_launches += 3;
+  ctx->stats.kernel_launches += 1;
   return FB200_OK;
 }
 

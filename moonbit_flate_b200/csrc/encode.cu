@@ -44,7 +44,7 @@ __device__ __forceinline__ BlockRef block_ref(const DeflateJob &j, uint64_t blk)
 __global__ void __launch_bounds__(256) k_histogram(DeflateJob j)
 {
   __shared__ uint32_t hist[kFreqStride];
-  const uint64_t blk = blockIdx.x;
+  const uint64_t blk = j.blk_begin + blockIdx.x;
   const BlockRef r = block_ref(j, blk);
   const uint32_t n = r.n;
   const uint32_t ntok = j.blk_ntok[blk];
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) k_histogram(DeflateJob j)
   if (kind == kKindDynamic) {
     const uint32_t *tok = j.tokens + r.src_off;
     for (uint32_t i = threadIdx.x; i < ntok; i += blockDim.x) {
-      const uint32_t t = tok[i];
+      const uint32_t t = __ldcs(tok + i); // streaming: read once here, once more by K4
       if (t < kMatchType) {
         atomicAdd(&hist[t], 1u);
       } else {
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(256) k_histogram(DeflateJob j)
 
 void launch_histogram(const DeflateJob &j, cudaStream_t st)
 {
-  if (j.nblocks == 0) return;
-  k_histogram<<<(unsigned)j.nblocks, 256, 0, st>>>(j);
+  if (j.blk_end <= j.blk_begin) return;
+  k_histogram<<<(unsigned)(j.blk_end - j.blk_begin), 256, 0, st>>>(j);
 }
 
 // ------------------------------------------------------------------
@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(DeflateJob j)
   HuffScratch &S = reinterpret_cast<HuffScratch *>(build_smem)[threadIdx.x >> 5];
   for (;;) { // blocks differ a lot in cost (alphabet size): hand them out one at a time
     uint32_t b32 = 0;
-    if ((threadIdx.x & 31) == 0) b32 = atomicAdd(&j.counters[10], 1u);
+    if ((threadIdx.x & 31) == 0) b32 = atomicAdd(j.work_counter, 1u);
     b32 = __shfl_sync(kFull, b32, 0);
-    if (b32 >= j.nblocks) break;
-    const uint64_t blk = b32;
+    if (j.blk_begin + b32 >= j.blk_end) break;
+    const uint64_t blk = j.blk_begin + b32;
     const int kind = j.blk_kind[blk];
     if (kind == kKindStored) continue;
     const BlockRef r = block_ref(j, blk);
@@ -117,100 +117,24 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(DeflateJob j)
   }
 }
 
-void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st)
+void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st, int warps_per_cta)
 {
-  if (j.nblocks == 0) return;
+  if (j.blk_end <= j.blk_begin) return;
   static bool inited = false;
-  const int smem = kBuildWarps * (int)sizeof(HuffScratch);
   if (!inited) {
-    cudaFuncSetAttribute(k_build_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_build_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildWarps * (int)sizeof(HuffScratch));
     inited = true;
   }
-  uint64_t want = (j.nblocks + kBuildWarps - 1) / kBuildWarps;
-  unsigned g = (unsigned)(want < (uint64_t)num_sms ? want : (uint64_t)num_sms);
-  k_build_codes<<<g, kBuildWarps * 32, smem, st>>>(j);
-}
-
-// ------------------------------------------------------------------
-// K2 + K3 fused, one warp per block, consuming the completion queue of the parse: the block policy and
-// histogram (k_histogram) go straight into the warp's shared-memory scratch, then the codes are built.
-// The kernel is co-resident with the (latency-bound) parse, so code construction costs no time of its own.
-constexpr int kPostWarpsMax = 4;
-
-__global__ void __launch_bounds__(kPostWarpsMax * 32) k_post(DeflateJob j)
-{
-  extern __shared__ __align__(16) uint8_t build_smem[];
-  HuffScratch &S = reinterpret_cast<HuffScratch *>(build_smem)[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(&j.counters[9], 1u);
-    t = __shfl_sync(kFull, t, 0);
-    if (t >= j.nblocks) break;
-    uint32_t v = 0;
-    if (lane == 0)
-      while ((v = *(volatile uint32_t *)&j.queue[t]) == 0) __nanosleep(300);
-    v = __shfl_sync(kFull, v, 0);
-    const uint64_t blk = v - 1u;
-    const BlockRef r = block_ref(j, blk);
-    const uint32_t n = r.n;
-    const uint32_t ntok = __ldcg(&j.blk_ntok[blk]);
-    int kind;
-    if (n <= 16) kind = kKindStored;                 // deflate.mbt:248-249
-    else if (n < 128) kind = kKindHuff;              // :250-252
-    else kind = (ntok > n - (n >> 4)) ? kKindHuff : kKindDynamic; // :266
-    if (kind == kKindStored) {
-      if (lane == 0) j.blk_kind[blk] = (uint8_t)kind;
-      continue;
-    }
-    for (int i = lane; i < 320; i += 32) S.freq[i] = 0;
-    __syncwarp();
-    if (kind == kKindDynamic) {
-      const uint32_t *tok = j.tokens + r.src_off;
-      for (uint32_t i = lane; i < ntok; i += 32) {
-        const uint32_t tk = __ldcg(tok + i);
-        if (tk < kMatchType) atomicAdd(&S.freq[tk], 1u);
-        else {
-          int lc, nb, oc;
-          uint32_t ex;
-          length_code_of((tk - kMatchType) >> kLengthShift, lc, nb, ex);
-          offset_code_of(tk & kOffsetMask, oc, nb, ex);
-          atomicAdd(&S.freq[kLenCodesStart + lc], 1u);
-          atomicAdd(&S.freq[kNumLit + oc], 1u);
-        }
-      }
-    } else {
-      const uint8_t *src = j.src + r.src_off;
-      for (uint32_t i = lane; i < n; i += 32) atomicAdd(&S.freq[__ldg(src + i)], 1u);
-    }
-    __syncwarp();
-    if (lane == 0) S.freq[kEob] = 1; // EOB: pushed token 256 (hbw:507) / literal_freq[256] = 1 (hbw:754)
-    __syncwarp();
-    const BlockBuild res = build_block_warp(nullptr, kind, n, j.blk_code + blk * kFreqStride, j.blk_hdr + blk * kHdrWords, S);
-    if (lane == 0) {
-      j.blk_kind[blk] = (uint8_t)res.kind;
-      j.blk_hdr_nbits[blk] = res.hdr_nbits;
-      j.blk_bits[blk] = res.blk_bits;
-    }
-    __syncwarp();
-  }
-}
-
-void launch_post(const DeflateJob &j, int num_sms, cudaStream_t st)
-{
-  if (j.nblocks == 0) return;
-  static bool inited = false;
-  static int warps = 3;
-  if (!inited) {
-    const char *e = getenv("FB200_POST_WARPS");
-    if (e && atoi(e) >= 1 && atoi(e) <= kPostWarpsMax) warps = atoi(e);
-    cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostWarpsMax * (int)sizeof(HuffScratch));
-    inited = true;
-  }
-  const int smem = warps * (int)sizeof(HuffScratch);
-  uint64_t want = (j.nblocks + warps - 1) / warps;
-  unsigned g = (unsigned)(want < (uint64_t)num_sms ? want : (uint64_t)num_sms);
-  k_post<<<g, warps * 32, smem, st>>>(j);
+  int w = warps_per_cta;
+  if (w < 1) w = 1;
+  if (w > kBuildWarps) w = kBuildWarps;
+  const int smem = w * (int)sizeof(HuffScratch);
+  // enough CTAs to fill the GPU when the kernel has it to itself (the blocks are handed out dynamically)
+  const uint64_t nb = j.blk_end - j.blk_begin;
+  const uint64_t want = (nb + w - 1) / w;
+  const uint64_t full = (uint64_t)num_sms * (uint64_t)(kBuildWarps / w);
+  const unsigned g = (unsigned)(want < full ? want : full);
+  k_build_codes<<<g, w * 32, smem, st>>>(j);
 }
 
 // ------------------------------------------------------------------
@@ -218,8 +142,8 @@ void launch_post(const DeflateJob &j, int num_sms, cudaStream_t st)
 // stored blocks, which pad to a byte after their 3 header bits, hbw:483-486).
 __global__ void k_layout(DeflateJob j)
 {
-  const uint64_t st = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (st >= j.nstreams) return;
+  const uint64_t st = j.st_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (st >= j.st_end) return;
   const uint64_t b0 = j.stream_blk0[st], b1 = j.stream_blk0[st + 1];
   const uint64_t L = j.stream_off[st + 1] - j.stream_off[st];
   uint64_t bit = 0;
@@ -240,8 +164,8 @@ __global__ void k_layout(DeflateJob j)
 
 void launch_layout(const DeflateJob &j, cudaStream_t st)
 {
-  if (j.nstreams == 0) return;
-  unsigned g = (unsigned)((j.nstreams + 127) / 128);
+  if (j.st_end <= j.st_begin) return;
+  unsigned g = (unsigned)((j.st_end - j.st_begin + 127) / 128);
   k_layout<<<g, 128, 0, st>>>(j);
 }
 
@@ -277,7 +201,8 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(DeflateJob j)
   __shared__ uint32_t wsum[kPackThreads / 32];
   __shared__ uint32_t carry_word;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t blk = blockIdx.x;
+  const uint64_t blk = j.blk_begin + blockIdx.x;
+  if (j.dst_off[j.st_end] > j.dst_cap) return; // the range does not fit: nothing is written, the host reports the need
   const BlockRef r = block_ref(j, blk);
   const int kind = j.blk_kind[blk];
   uint32_t *dst32 = reinterpret_cast<uint32_t *>(j.dst);
@@ -334,7 +259,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(DeflateJob j)
         if (i < nitems) {
           uint32_t t;
           if (i == nitems - 1) t = kEob;
-          else t = (kind == kKindDynamic) ? tok[i] : (uint32_t)__ldg(src + i);
+          else t = (kind == kKindDynamic) ? __ldcs(tok + i) : (uint32_t)__ldg(src + i);
           if (t < kMatchType) { // literal / EOB (hbw:609-612)
             const uint32_t e = codes[t];
             val[k] = e & 0xffff;
@@ -387,7 +312,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(DeflateJob j)
     for (uint32_t i = tid; i < nfull; i += kPackThreads) {
       const uint64_t gw = gw0 + i;
       const uint32_t v = stage[i];
-      if (gw * 32 >= B0 && (gw + 1) * 32 <= B1) dst32[gw] = v;
+      if (gw * 32 >= B0 && (gw + 1) * 32 <= B1) __stcs(&dst32[gw], v);
       else if (v) atomicOr(&dst32[gw], v);
     }
     if (tid == 0) carry_word = stage[nfull];
@@ -409,8 +334,8 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(DeflateJob j)
 // bits 1,0,0 then pad to a byte, then 00 00 FF FF.
 __global__ void k_trailer(DeflateJob j)
 {
-  const uint64_t st = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (st >= j.nstreams) return;
+  const uint64_t st = j.st_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (st >= j.st_end || j.dst_off[j.st_end] > j.dst_cap) return;
   uint32_t *dst32 = reinterpret_cast<uint32_t *>(j.dst);
   const uint64_t bit = j.dst_off[st] * 8 + j.stream_trailer_bit[st];
   atomicOr(&dst32[bit >> 5], 1u << (bit & 31));
@@ -421,11 +346,41 @@ __global__ void k_trailer(DeflateJob j)
 
 void launch_pack(const DeflateJob &j, cudaStream_t st)
 {
-  if (j.nblocks) k_pack<<<(unsigned)j.nblocks, kPackThreads, 0, st>>>(j);
-  if (j.nstreams) {
-    unsigned g = (unsigned)((j.nstreams + 127) / 128);
+  if (j.blk_end > j.blk_begin) k_pack<<<(unsigned)(j.blk_end - j.blk_begin), kPackThreads, 0, st>>>(j);
+  if (j.st_end > j.st_begin) {
+    unsigned g = (unsigned)((j.st_end - j.st_begin + 127) / 128);
     k_trailer<<<g, 128, 0, st>>>(j);
   }
+}
+
+// K4 ORs its bits into the output: the words of the range are cleared first.  Ranges are packed in order and a
+// 32-bit word may be shared by the last stream of one range and the first of the next; it belongs to the earlier
+// range (a range clears from the word boundary at or above its start to the word boundary at or above its end).
+__global__ void __launch_bounds__(256) k_zero_range(DeflateJob j)
+{
+  if (j.dst_off[j.st_end] > j.dst_cap) return;
+  const uint64_t a = (j.dst_off[j.st_begin] + 3) >> 2, b = (j.dst_off[j.st_end] + 3) >> 2; // words
+  uint32_t *dst32 = reinterpret_cast<uint32_t *>(j.dst);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b - a < 64) {
+    for (uint64_t k = a + t; k < b; k += stride) dst32[k] = 0;
+    return;
+  }
+  // 16-byte stores between (aligned on the address, dst itself is only 4-byte aligned), single words at the ends
+  const uint64_t bw = (reinterpret_cast<uintptr_t>(j.dst) >> 2) & 3;
+  const uint64_t a4 = ((a + bw + 3) & ~3ull) - bw, b4 = ((b + bw) & ~3ull) - bw;
+  for (uint64_t k = a + t; k < a4; k += stride) dst32[k] = 0;
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst32 + a4);
+  const uint64_t n4 = (b4 - a4) >> 2;
+  for (uint64_t k = t; k < n4; k += stride) __stcs(&d4[k], make_uint4(0, 0, 0, 0));
+  for (uint64_t k = b4 + t; k < b; k += stride) dst32[k] = 0;
+}
+
+void launch_zero_range(const DeflateJob &j, cudaStream_t st)
+{
+  if (j.st_end <= j.st_begin) return;
+  k_zero_range<<<296, 256, 0, st>>>(j);
 }
 
 // CUDA loads kernels lazily, and loading one while another kernel spins on a host-fed watermark can
@@ -435,7 +390,7 @@ void preload_encode_kernels()
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_histogram);
   cudaFuncGetAttributes(&a, k_build_codes);
-  cudaFuncGetAttributes(&a, k_post);
+  cudaFuncGetAttributes(&a, k_zero_range);
   cudaFuncGetAttributes(&a, k_layout);
   cudaFuncGetAttributes(&a, k_pack);
   cudaFuncGetAttributes(&a, k_trailer);

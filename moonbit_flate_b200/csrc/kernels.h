@@ -35,10 +35,10 @@ struct DeflateJob {
   // host-buffer calls: number of streams whose bytes have arrived (advanced by the H2D stream after
   // every chunk); the parse waits on it, so the copy overlaps the kernel.  Null: everything is resident.
   const uint32_t *avail;
-  // finished blocks, in completion order (entry = block index + 1; counters[8] = tail, counters[9] = head):
-  // the parse publishes every block here so that k_post can build its codes while later blocks are still
-  // being parsed.  Null: K2/K3 run as separate kernels after the parse.
-  uint32_t *queue;
+  // range the post-parse kernels work on in this launch (whole batch: 0..nblocks / 0..nstreams)
+  uint64_t blk_begin, blk_end, st_begin, st_end;
+  uint32_t *work_counter;        // K3 work distribution of this launch (zeroed by the host)
+  uint64_t dst_cap;              // K4 writes nothing for a range that would end beyond it (host reports the need)
   // output
   uint8_t *dst;
 };
@@ -55,16 +55,22 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st);
 void launch_histogram(const DeflateJob &j, cudaStream_t st);
 // K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,
 //     huffman-bit-writer.mbt:241-471)
-void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st);
-// K2 + K3 per block, fed by DeflateJob::queue; runs beside the parse on its own stream
-void launch_post(const DeflateJob &j, int num_sms, cudaStream_t st);
+void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st, int warps_per_cta = 10);
 // layout: per-stream bit offsets, stream sizes, output offsets
 void launch_layout(const DeflateJob &j, cudaStream_t st);
 // K4: bit packing (huffman-bit-writer.mbt:596-824, :474-487) + stream trailers
 void launch_pack(const DeflateJob &j, cudaStream_t st);
+// clears the output words of streams [st_begin, st_end) (K4 ORs into them); a word shared with the previous
+// range belongs to that range's clear
+void launch_zero_range(const DeflateJob &j, cudaStream_t st);
+// out[i] = in[min(i * stride, n)], i in [0, cnt): group boundaries of an offset array
+void launch_gather_u64(uint64_t *out, const uint64_t *in, uint64_t stride, uint64_t n, uint64_t cnt, cudaStream_t st);
 
-// exclusive scan of n uint64 values (out may alias in); out has n+1 entries
-void launch_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n, cudaStream_t st);
+// exclusive scan of n uint64 values (out may alias in); out has n+1 entries.  carry_from: start value read
+// from device memory (may be out itself: the total the previous range's scan left there), or null for 0
+// host_total: pinned host memory that receives the total as well (written by the kernel itself), or null
+void launch_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n, cudaStream_t st, const uint64_t *carry_from = nullptr,
+                     uint64_t *host_total = nullptr);
 // fixed-size segment offsets: off[i] = min(i*seg, n), i in [0, nseg]
 void launch_fill_seg_off(uint64_t *off, uint64_t nseg, uint64_t seg, uint64_t n, cudaStream_t st);
 
