@@ -457,6 +457,11 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t 
     if (rc != FB200_OK) return rc;
   }
 
+  if (parse_uses_l2_persistence()) { // experiment switch: un-pin the tables before anything else runs
+    CK(cudaStreamSynchronize(st));
+    parse_release_l2();
+  }
+
   // K2 .. K4 of one group on stream sp
   auto launch_group = [&](uint64_t g, cudaStream_t sp, bool chain) -> int {
     DeflateJob jg = j;

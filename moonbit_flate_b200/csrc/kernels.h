@@ -51,6 +51,9 @@ void launch_count_blocks(const DeflateJob &j, cudaStream_t st);
 void launch_fill_blocks(const DeflateJob &j, cudaStream_t st);
 // K1: greedy LZ77 parse, one warp per stream (deflate-fast.mbt:123-342)
 void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st);
+// FB200_PARSE_L2PERSIST=1 only: to be called once the parse has completed (un-pins its L2 lines); returns at once otherwise
+void parse_release_l2();
+bool parse_uses_l2_persistence();
 // K2: block kind + histograms (huffman-bit-writer.mbt:550-593, :831)
 void launch_histogram(const DeflateJob &j, cudaStream_t st);
 // K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,

@@ -295,7 +295,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           if (lane == 0 && pos + 256 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + pos + 256));
           const uint32_t h = hash4(cv);
           T *slot = table + h;
-          const T old = *slot;
+          const T old = *slot; // (ld.global.cg for the global tables: measured, no difference)
           const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
           T la_old = 0;
           bool la_ok = false;
@@ -548,6 +548,16 @@ void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
 // batch.  Compiled out by default.
 static int g_parse_occ_single = 0, g_parse_occ_multi = 0, g_parse_gwarps = 0, g_parse_wide = 0;
 static void *g_parse_gtables = nullptr;
+static int g_parse_persist = -1;
+
+// After the parse has finished: lines the persistence window pinned in L2 go back to normal, so that the
+// set-aside part of L2 serves the kernels that follow (left pinned, it cost the inflate 2.4 ms per GiB).
+bool parse_uses_l2_persistence() { return g_parse_persist > 0; }
+
+void parse_release_l2()
+{
+  if (g_parse_persist > 0) cudaCtxResetPersistingL2Cache();
+}
 
 void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
 {
@@ -590,7 +600,7 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
   }
   // keep the global-memory tables resident in L2 (they are hit at random, 2 bytes at a time) while the
   // source and the token stream flow through
-  static int persist = -1;
+  int &persist = g_parse_persist;
   if (persist < 0) {
     const char *e = getenv("FB200_PARSE_L2PERSIST");
     persist = e ? atoi(e) : 0;
