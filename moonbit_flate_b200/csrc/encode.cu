@@ -91,7 +91,7 @@ void launch_histogram(const DeflateJob &j, cudaStream_t st)
 
 // ------------------------------------------------------------------
 // K3: code construction.  One warp per block, working set in shared memory (huff_build.cuh).
-constexpr int kBuildWarps = 10;
+constexpr int kBuildWarps = 18; // 11.8 KB of scratch per warp
 
 __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(DeflateJob j)
 {

@@ -84,6 +84,7 @@ FB_HD inline int wmax(int v)
 
 constexpr int kMaxSyms = 288;
 constexpr int kSortPad = 512;
+constexpr int kMaskWords = 2 * kMaxSyms / 32; // one bit per list position
 
 // Per-warp working set (shared memory on the device).
 struct HuffScratch {
@@ -91,7 +92,8 @@ struct HuffScratch {
   uint32_t lista[2 * kMaxSyms];     // package-merge lists (weights), double buffered
   uint32_t listb[2 * kMaxSyms];
   uint32_t pairs[kMaxSyms];
-  uint16_t leafpos[16][kMaxSyms];   // position of leaf i in list_k
+  uint32_t leafmask[16][kMaskWords]; // bit p set: item p of list_k is a leaf (1.1 KB instead of 9 KB of leaf positions:
+                                    // the warp's scratch is what caps the kernel's occupancy)
   uint32_t run[16];                 // canonical code counters
   // block assembly
   uint32_t freq[320];               // lit/len (286) ++ offset (30) histogram
@@ -131,7 +133,7 @@ __device__ __forceinline__ void pm_merge_level(HuffScratch &S, int k, int n, int
     const int i = FB_LANE + 32 * q;
     if (i < n) {
       const int pos = i + lo[q];
-      S.leafpos[k][i] = (uint16_t)pos;
+      atomicOr(&S.leafmask[k][pos >> 5], 1u << (pos & 31));
       if (pos < cap) cur[pos] = w[q];
     }
   }
@@ -233,6 +235,7 @@ FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, ui
   const int mb = max_bits < n - 1 ? max_bits : n - 1; // :126-129
   const int cap = 2 * n - 2;
   uint32_t *prev = S.lista, *cur = S.listb;
+  FB_PFOR(i, 16 * kMaskWords) (&S.leafmask[0][0])[i] = 0;
   FB_PFOR(i, n) prev[i] = S.keys[i] >> 9;
   int plen = n;
   FB_WSYNC();
@@ -254,7 +257,7 @@ FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, ui
         if (S.pairs[mid] <= w) lo = mid + 1; else hi = mid;
       }
       const int pos = i + lo;
-      S.leafpos[k][i] = (uint16_t)pos;
+      S.leafmask[k][pos >> 5] |= 1u << (pos & 31);
       if (pos < cap) cur[pos] = w;
     }
     FB_PFOR(j, np) { // pair j sits after every leaf of weight < its own
@@ -281,13 +284,24 @@ FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, ui
     for (int k = mb; k >= 1; k--) {
       int lv;
       if (k == 1) lv = m < n ? m : n;
-      else {
-        int lo = 0, hi = n;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if ((int)S.leafpos[k][mid] < m) lo = mid + 1; else hi = mid;
+      else { // leaves among the first m items of list_k
+#if defined(__CUDA_ARCH__)
+        const int wi = FB_LANE;
+        int c = 0;
+        if (wi < kMaskWords) {
+          const int lo_bit = 32 * wi;
+          const unsigned sel = m >= lo_bit + 32 ? 0xffffffffu : (m > lo_bit ? ((1u << (m - lo_bit)) - 1u) : 0u);
+          c = __popc(S.leafmask[k][wi] & sel);
         }
-        lv = lo;
+        lv = __reduce_add_sync(0xffffffffu, c);
+#else
+        lv = 0;
+        for (int wi = 0; wi < kMaskWords; wi++) {
+          const int lo_bit = 32 * wi;
+          const unsigned sel = m >= lo_bit + 32 ? 0xffffffffu : (m > lo_bit ? ((1u << (m - lo_bit)) - 1u) : 0u);
+          lv += __builtin_popcount(S.leafmask[k][wi] & sel);
+        }
+#endif
       }
       nl[k] = lv;
       m = 2 * (m - lv);

@@ -58,7 +58,7 @@ bool parse_uses_l2_persistence();
 void launch_histogram(const DeflateJob &j, cudaStream_t st);
 // K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,
 //     huffman-bit-writer.mbt:241-471)
-void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st, int warps_per_cta = 10);
+void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st, int warps_per_cta = 18);
 // layout: per-stream bit offsets, stream sizes, output offsets
 void launch_layout(const DeflateJob &j, cudaStream_t st);
 // K4: bit packing (huffman-bit-writer.mbt:596-824, :474-487) + stream trailers
