@@ -265,6 +265,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # host buffers next to the GPU: bind this rank to the CPUs NVML reports as local to its GPU before any pinned
+    # allocation (first touch decides the NUMA node); without it the e2e copies of several ranks cross sockets
+    affinity = "unchanged"
+    if os.environ.get("FB200_BENCH_AFFINITY", "1") != "0":
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            affinity = f"nvml ideal cpus ({len(os.sched_getaffinity(0))} cpus)"
+        except Exception as e:  # noqa: BLE001 -- restricted cpusets: keep the default placement
+            affinity = f"unchanged ({type(e).__name__})"
+    config["host_affinity"] = affinity
+
     ctx = fb.Context(local_rank)
     lib_stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=dev)
 

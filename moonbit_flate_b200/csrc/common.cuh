@@ -18,6 +18,7 @@ constexpr int kMaxMatchOffset = 1 << 15;        // :40
 constexpr int kMaxMatchLength = 258;            // :34
 constexpr int kBlockSize = 65535;               // max_store_block_size :46
 constexpr int kInputMargin = 15;                // :89
+constexpr int kBufferReset = 2147483647 - 2 * kBlockSize; // buffer_reset :55
 constexpr uint32_t kMatchType = 1u << 30;       // token.mbt:24
 constexpr int kLengthShift = 22;                // token.mbt:13
 constexpr uint32_t kOffsetMask = (1u << kLengthShift) - 1;

@@ -136,14 +136,29 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
 
     const uint64_t blk0 = j.stream_blk0[st32];
     const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
+    // DeflateFast.cur (:95-117): 65535 at the start, + the block length after every block.  When it reaches
+    // buffer_reset (about every 2 GiB of one stream) encode calls shift_offsets (:129-132), which -- `prev` being
+    // always empty, D1 -- clears the table and restarts cur at 32769 (:366-374).  Table positions are kept
+    // relative to the last such point, so they neither wrap nor collide with the "empty" value.
+    int64_t ref_cur = kBlockSize;
+    uint64_t pos_base = 0;
     uint32_t b = 0;
     for (; b < nblk; b++) {
       const uint64_t boff = (uint64_t)b * kBlockSize;
       const int n = (int)((L - boff) < (uint64_t)kBlockSize ? (L - boff) : (uint64_t)kBlockSize);
       if (n < 128) break; // small tail: not parsed (deflate.mbt:244-257)
+      if (MULTI && ref_cur >= (int64_t)kBufferReset) {
+        uint4 *t4 = reinterpret_cast<uint4 *>(table);
+        const int n4 = (int)(kTableSize * sizeof(T) / 16);
+        for (int i = lane; i < n4; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        ref_cur = kMaxMatchOffset + 1;
+        pos_base = boff;
+      }
+      ref_cur += n;
       const uint8_t *srcb = j.src + o0 + boff;
       uint32_t *tok = j.tokens + o0 + boff;
-      const uint32_t S0 = (uint32_t)boff; // stream-relative block start (MULTI)
+      const uint32_t S0 = (uint32_t)(boff - pos_base); // block start relative to the last table reset (MULTI)
       const int s_limit = n - kInputMargin;
 
       int s = 0, next_emit = 0;

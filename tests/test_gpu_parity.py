@@ -1,5 +1,6 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI, against the
 CPU oracle on the same seeded inputs (bit-exact: integer / byte work)."""
+import os
 import zlib
 
 import numpy as np
@@ -354,3 +355,25 @@ def test_peer_frame_single_rank(ctx, corpus):
     assert np.array_equal(sizes_f.numpy(), np.diff(off).astype(np.int64))
     assert np.array_equal(pf.view[hdr:total].cpu().numpy(), comp)
     pf.close()
+
+
+@pytest.mark.skipif(os.environ.get("FB200_SLOW_TESTS") != "1",
+                    reason="6 minutes: a single 2.1 GiB stream is one warp's serial work (set FB200_SLOW_TESTS=1); "
+                           "passed on B200 on 2026-10-18, see DESIGN.md")
+def test_stream_beyond_2gib_table_reset(ctx, oracle, corpus):
+    """One stream longer than buffer_reset (deflate-fast.mbt:55, :129-132): about 2 GiB into a stream
+    DeflateFast.cur reaches buffer_reset and shift_offsets clears the hash table (prev is always empty, D1), so
+    the block that follows finds no 4-byte matches into its predecessor.  The GPU stream must equal the
+    oracle's byte for byte (the oracle restates shift_offsets), and inflate back."""
+    nblk = 32770  # the reset happens at the start of block 32767
+    n = nblk * 65535 + 777
+    src = corpus.fill((n + 65535) // 65536, 65536, seed=77, klass=Corpus.TEXT)[:n]
+    off = np.array([0, n], dtype=np.uint64)
+    comp, doff = ctx.deflate_streams(src, off)
+    want = np.frombuffer(oracle.deflate(src), dtype=np.uint8)
+    assert comp.size == want.size
+    assert np.array_equal(comp, want)
+    del want
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, doff, off)
+    assert int(st[0]) == 0 and int(olen[0]) == n and int(cons[0]) == comp.size
+    assert np.array_equal(out, src)
