@@ -83,6 +83,10 @@ struct fb200_ctx {
   bool pipeline = true;
   uint64_t group_bytes = 64ull << 20;
   static constexpr int kMaxGroups = 256;
+  // block-parallel parse of multi-block streams (FB200_PARSE_BLOCKPAR: 0 never, 1 when there are few such
+  // streams (default), 2 always)
+  int blockpar = 1;
+  DevBuf bp_flags, bp_idx, bp_tabs, bp_state, bp_list;
   DevBuf d_group;                 // [kMaxGroups] u32: K3 work counters
   DevBuf d_group_bounds;          // [kMaxGroups + 1] u64: first block of every group
   uint64_t *h_gbounds = nullptr;  // pinned [kMaxGroups + 1] block bounds, [kMaxGroups + 1] output byte offsets
@@ -115,6 +119,10 @@ struct fb200_ctx {
   } while (0)
 
 extern "C" int fb200_version(void) { return FB200_VERSION; }
+
+// test hook (not part of the public header): the closed form the block-parallel parse uses for "this block starts
+// with a cleared table" (deflate-fast.mbt:129-132)
+extern "C" int fb200_debug_block_resets(uint64_t b) { return block_resets_table(b) ? 1 : 0; }
 
 extern "C" int fb200_create(fb200_ctx **out, int device)
 {
@@ -162,6 +170,7 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   cudaEventCreateWithFlags(&ctx->e_bounds, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->e_parsed, cudaEventDisableTiming);
   if (const char *e = getenv("FB200_DEFLATE_PIPELINE")) ctx->pipeline = atoi(e) != 0;
+  if (const char *e = getenv("FB200_PARSE_BLOCKPAR")) ctx->blockpar = atoi(e);
   if (const char *e = getenv("FB200_GROUP_MB")) {
     const long mb = atol(e);
     if (mb > 0) ctx->group_bytes = (uint64_t)mb << 20;
@@ -216,6 +225,7 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
   }
   ctx->group_done.release();
   ctx->d_group.release();
+  for (DevBuf *b : {&ctx->bp_flags, &ctx->bp_idx, &ctx->bp_tabs, &ctx->bp_state, &ctx->bp_list}) b->release();
   ctx->d_group_bounds.release();
   for (auto *v : {&ctx->e_gsize, &ctx->e_gdone, &ctx->e_gchain})
     for (cudaEvent_t e : *v) cudaEventDestroy(e);
@@ -341,6 +351,7 @@ struct DeflateIo {
   uint64_t ns = 0, n_total = 0;
   uint64_t *d_dst_off = nullptr;       // device [ns + 1]
   uint64_t nb_known = ~0ull;           // number of blocks if the caller knows it, else read back
+  uint64_t n_multi = 0, nmb = 0;       // (with nb_known) streams of more than one parsed block, and their blocks
   const uint32_t *avail = nullptr;     // arrival watermark (host-buffer calls)
   uint8_t *d_dst = nullptr;            // device output (4-byte aligned)
   uint64_t d_cap = 0;                  // its capacity in bytes
@@ -412,10 +423,15 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t 
   CK(cudaMemcpyAsync(h_bb, ctx->d_group_bounds.p, (ngroups + 1) * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ctx->e_bounds, st));
   launches += 3;
-  uint64_t nb = io.nb_known;
+  uint64_t nb = io.nb_known, n_multi = io.n_multi, nmb = io.nmb;
   if (nb == ~0ull) {
+    launch_count_multi(j, st); // -> counters[12] streams, counters[13] blocks (saturating)
+    CK(cudaMemcpyAsync(ctx->pinned + 16, j.counters + 12, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     nb = h_bb[ngroups];
+    const uint32_t *cm = reinterpret_cast<const uint32_t *>(ctx->pinned + 16);
+    n_multi = cm[0];
+    nmb = cm[1];
   }
   if (nb > 0x7fffffffull) { ctx->err = "too many blocks in one call"; return FB200_ERR_ARG; }
   j.nblocks = nb;
@@ -448,14 +464,62 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t 
   ctx->stage_end(FB200_STAGE_SETUP);
 
   ctx->stage_begin(FB200_STAGE_PARSE);
-  launch_parse(j, ctx->num_sms, st);
-  ctx->stage_end(FB200_STAGE_PARSE);
-  launches += 2;
+  launch_parse_single(j, ctx->num_sms, st);
+  launches += 1;
   CK(cudaGetLastError());
   {
     const int rc = feed(); // host-buffer calls: queue the H2D chunks + watermark updates
     if (rc != FB200_OK) return rc;
   }
+  const bool blockpar = n_multi > 0 && (ctx->blockpar == 2 || (ctx->blockpar == 1 && n_multi < 4096));
+  if (n_multi > 0 && !blockpar) {
+    launch_parse_multi(j, ctx->num_sms, st); // one warp per stream, its blocks in sequence
+    launches += 1;
+  } else if (blockpar) {
+    // rounds over the blocks of the multi-block streams (BlockParJob, kernels.h)
+    CK(ctx->bp_flags.ensure((nb + 1) * 8));
+    CK(ctx->bp_idx.ensure((nb + 1) * 8));
+    launch_bp_flags(j, ctx->bp_flags.as<uint64_t>(), st);
+    launch_scan_u64(ctx->bp_flags.as<uint64_t>(), ctx->bp_idx.as<uint64_t>(), nb, st);
+    CK(cudaMemcpyAsync(ctx->pinned + 17, ctx->bp_idx.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nmb = ctx->pinned[17];
+    CK(ctx->bp_tabs.ensure(2 * nmb * (uint64_t)kTableSize * 2));
+    CK(ctx->bp_state.ensure(4 * nmb + 16)); // lat[2][nmb], chg[2][nmb]
+    CK(ctx->bp_list.ensure(nmb * 4 + 16));
+    uint8_t *lat = ctx->bp_state.as<uint8_t>(), *chg = lat + 2 * nmb;
+    CK(cudaMemsetAsync(lat, 0, 4 * nmb, st)); // round 1 reads "latest copy = 0" for every block
+    BlockParJob bp{};
+    bp.list = ctx->bp_list.as<uint32_t>();
+    bp.mb_idx = ctx->bp_idx.as<uint64_t>();
+    bp.tabs = ctx->bp_tabs.as<uint16_t>();
+    bp.nmb = nmb;
+    uint32_t *h_nlist = reinterpret_cast<uint32_t *>(ctx->pinned + 18);
+    uint64_t rounds = 0, parsed_blocks = 0;
+    for (int round = 1;; round++) {
+      bp.round = round;
+      bp.lat_prev = lat + (size_t)((round - 1) & 1) * nmb;
+      bp.lat_next = lat + (size_t)(round & 1) * nmb;
+      bp.chg_next = chg + (size_t)(round & 1) * nmb;
+      CK(cudaMemsetAsync(j.counters + 13, 0, 8, st)); // [13] list length, [14] work counter of the round
+      launch_bp_round(j, bp, chg + (size_t)((round - 1) & 1) * nmb, ctx->bp_list.as<uint32_t>(), j.counters + 13, st);
+      CK(cudaMemcpyAsync(h_nlist, j.counters + 13, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      launches += 1;
+      if (*h_nlist == 0) break;
+      bp.nlist = *h_nlist;
+      launch_parse_blocks(j, bp, j.counters + 14, ctx->num_sms, st);
+      launches += 1;
+      rounds++;
+      parsed_blocks += bp.nlist;
+      if ((uint64_t)round > nmb + 2) { ctx->err = "internal error: block-parallel parse does not converge"; return FB200_ERR_CUDA; }
+    }
+    CK(cudaGetLastError());
+    if (getenv("FB200_TRACE"))
+      fprintf(stderr, "[fb200] block-parallel parse: %llu streams, %llu blocks, %llu rounds, %llu block parses\n",
+              (unsigned long long)n_multi, (unsigned long long)nmb, (unsigned long long)rounds, (unsigned long long)parsed_blocks);
+  }
+  ctx->stage_end(FB200_STAGE_PARSE);
 
   if (parse_uses_l2_persistence()) { // experiment switch: un-pin the tables before anything else runs
     CK(cudaStreamSynchronize(st));
@@ -615,7 +679,7 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
   // chunks of whole streams + number of blocks (deflate.mbt:222-229: one block per 65535 bytes)
   struct Cut { uint64_t streams, bytes; }; // streams / bytes delivered once this chunk has arrived
   std::vector<Cut> cuts;
-  uint64_t nb = 0;
+  uint64_t nb = 0, n_multi = 0, nmb = 0;
   uint64_t step = ctx->chunk_bytes;
   if (n / step + 2 > (uint64_t)fb200_ctx::kMaxChunks) step = n / (fb200_ctx::kMaxChunks - 2) + 1;
   if (src_off) {
@@ -623,6 +687,7 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
     for (uint64_t i = 0; i < ns; i++) {
       const uint64_t len = src_off[i + 1] - src_off[i];
       nb += (len + kBlockSize - 1) / kBlockSize;
+      if (len >= (uint64_t)kBlockSize + 128) { n_multi++; nmb += (len + kBlockSize - 1) / kBlockSize; }
       const uint64_t endb = src_off[i + 1] - base0;
       if (endb >= next_cut || i + 1 == ns) {
         cuts.push_back({i + 1, endb});
@@ -638,6 +703,8 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
     }
     const uint64_t full = n / seg_size, tail = n % seg_size;
     nb = full * ((seg_size + kBlockSize - 1) / kBlockSize) + (tail + kBlockSize - 1) / kBlockSize;
+    if (seg_size >= (uint64_t)kBlockSize + 128) { n_multi += full; nmb += full * ((seg_size + kBlockSize - 1) / kBlockSize); }
+    if (tail >= (uint64_t)kBlockSize + 128) { n_multi++; nmb += (tail + kBlockSize - 1) / kBlockSize; }
   }
   CK(ctx->p_in[0].ensure(n + 256));
   CK(ctx->p_off_in[0].ensure((ns + 1) * 8));
@@ -668,6 +735,8 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
   io.n_total = n;
   io.d_dst_off = ctx->p_off_out[0].as<uint64_t>();
   io.nb_known = nb;
+  io.n_multi = n_multi;
+  io.nmb = nmb;
   io.avail = ctx->d_wm;
   io.d_dst = ctx->p_out[0].as<uint8_t>();
   io.d_cap = dcap;

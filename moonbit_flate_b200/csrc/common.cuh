@@ -28,6 +28,14 @@ constexpr int kNumCodegen = 19;                 // huffman-bit-writer.mbt:26
 constexpr int kEob = 256;                       // :16
 constexpr int kLenCodesStart = 257;             // :21
 
+// DeflateFast.cur is 65535 before block 0 and grows by the block length; encode clears the table when it has
+// reached buffer_reset (:129-132): at the start of block 32766 (65535 * 32767 >= buffer_reset), and then, cur
+// restarting at 32769, every 32766 blocks again (checked against the running sum by tests/test_abi.py through fb200_debug_block_resets).
+__host__ __device__ inline bool block_resets_table(uint64_t b)
+{
+  return b != 0 && b % 32766 == 0;
+}
+
 // block kinds (deflate.mbt:236-277)
 constexpr int kKindStored = 0;   // n <= 16
 constexpr int kKindHuff = 1;     // 17 <= n <= 127, or tokens > n - n/16

@@ -28,6 +28,7 @@
 #include "kernels.h"
 #include "../../include/flate_b200.h"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace fb {
@@ -294,7 +295,9 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
         const uint32_t e2 = lds_u16(lit_sa + (((bits >> (cl + c1)) & ((1u << kLB) - 1u)) << 1));
         const uint32_t c2 = e2 & 15u, s2 = e2 >> 4;
         const uint32_t ab1 = ab0 + c1;
-        const bool three = two && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
+        // (the third look-up needs its 10 index bits inside the 32-bit peek: cl + c1 <= 22; that also keeps the
+        // bits dropped per step <= 32, which is all LBits::drop can move in one call)
+        const bool three = two && cl + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
         if (WRITE) {
           op[cnt_out] = (uint8_t)sym;
           if (two) op[cnt_out + 1] = (uint8_t)s1;
@@ -385,7 +388,7 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
         const uint32_t e2 = lds_u16(lit_sa + (((bits >> (c0 + c1)) & ((1u << kLB) - 1u)) << 1));
         const uint32_t c2 = e2 & 15u, s2 = e2 >> 4;
         const uint32_t ab1 = ab0 + c1;
-        const bool three = two && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
+        const bool three = two && c0 + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
         if (WRITE) {
           op[cnt_out] = (uint8_t)s0;
           if (two) op[cnt_out + 1] = (uint8_t)s1;
@@ -509,12 +512,16 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
     ub.init(in, in_len);
     bool bail = in_len > 0x0fffffffull; // keep bit positions comfortably inside 32 bits
     bool done = false;
+    uint32_t win_bits = j.window_bits ? j.window_bits : 96u * 1024u * 8u; // first block: a 65535-byte block fits
 
     while (!bail && !done) {
       // ---- block header (all lanes, uniform): next_block (inflate.mbt:345-379) ----
       ub.refill();
       const int final_flag = (int)ub.take(1);
       const int typ = (int)ub.take(2);
+#ifdef FB_INFLATE_DEBUG
+      if (lane == 0 && opos > 102800000u) printf("hdr: opos=%u final=%d typ=%d cur_len=%lld in_off=%lld nrec=%u win=%u\n", opos, final_flag, typ, (long long)cur_len, (long long)(in - in0), nrec, win_bits);
+#endif
       if (typ == 3) { bail = true; break; }
       if (typ == 0) { // stored block (data_block / copy_data, :708-766)
         const int64_t p = (ub.consumed_bits(in) + 7) >> 3;
@@ -607,64 +614,95 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
       }
 
       // ---- block body: 32 ranges, speculative starts, fixpoint over the hand-over positions ----
+      // The ranges are cut from a WINDOW of the input behind the header, not from all that is left of the stream:
+      // where the block ends is not known, and in a stream of many blocks everything behind its EOB would be
+      // decoded for nothing (a 64 MiB stream spent 15 ms per block that way).  The window is the whole rest for a
+      // stream that is about one block long, otherwise 1.25 x the size of the previous block; a block that is
+      // longer than its window simply goes on with another window behind it (same tables).
       const int64_t b0s = ub.consumed_bits(in);
       if (b0s >= cur_len * 8) { bail = true; break; }
-      const uint32_t b0 = (uint32_t)b0s, bend = (uint32_t)(cur_len * 8);
-      uint32_t R = (bend - b0 + 31u) / 32u;
-      if (R < kMinRange) R = kMinRange;
-      const uint64_t s64 = (uint64_t)b0 + (uint64_t)lane * R;
-      const uint32_t s_nom = s64 < bend ? (uint32_t)s64 : bend;
-      const uint32_t e_i = (s64 + R < bend) ? (uint32_t)(s64 + R) : bend;
-      // Round 0 only has to find where each lane leaves its range, and a wrong start falls onto true symbol
-      // boundaries within a few dozen symbols: every lane decodes just the last kSyncBits of their range (the
-      // whole range when most codes have the same length, which synchronises poorly).  A lane that did not
-      // synchronise is caught by the fixpoint below like any other wrong hand-over.
-      uint32_t start = s_nom, p = 0, flag = P_OK, n_out = 0, n_rec = 0;
-      if (!flat_code && e_i - s_nom > kSyncBits) start = e_i - kSyncBits; // lane 0 too: its full pass is round 1
-      bool need = true;
-      for (int round = 0; round < 34; round++) {
-        uint32_t tp, tf, to, tr = 0;
-        if (lit_only) decode_ranges_lit<false>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u);
-        else decode_ranges<false>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, need, start, e_i, tp, tf, to, tr,
-                                  nullptr, 0u, nullptr);
-        if (need) { p = tp; flag = tf; n_out = to; n_rec = tr; }
-        const uint32_t pp = __shfl_up_sync(kFull, p, 1);
-        const uint32_t pf = __shfl_up_sync(kFull, flag, 1);
-        const uint32_t ns = lane == 0 ? b0 : (pf == P_OK ? pp : start);
-        need = ns != start;
-        start = ns;
-        if (lane == 0) atomicAdd(&j.counters[5], 1u); // instrumentation: decode rounds
-        if (!__any_sync(kFull, need)) break;
+      uint32_t b0 = (uint32_t)b0s;
+      const uint32_t bend = (uint32_t)(cur_len * 8), blk_first_bit = b0;
+      uint32_t eob = 0;
+      for (bool have_eob = false; !have_eob;) {
+        const uint32_t wend = (uint64_t)b0 + win_bits < bend ? b0 + win_bits : bend;
+        uint32_t R = (wend - b0 + 31u) / 32u;
+        if (R < kMinRange) R = kMinRange;
+        const uint64_t s64 = (uint64_t)b0 + (uint64_t)lane * R;
+        const uint32_t s_nom = s64 < wend ? (uint32_t)s64 : wend;
+        const uint32_t e_i = (s64 + R < wend) ? (uint32_t)(s64 + R) : wend;
+        // Round 0 only has to find where each lane leaves its range, and a wrong start falls onto true symbol
+        // boundaries within a few dozen symbols: every lane decodes just the last kSyncBits of their range (the
+        // whole range when most codes have the same length, which synchronises poorly).  A lane that did not
+        // synchronise is caught by the fixpoint below like any other wrong hand-over.
+        uint32_t start = s_nom, p = 0, flag = P_OK, n_out = 0, n_rec = 0;
+        if (!flat_code && e_i - s_nom > kSyncBits) start = e_i - kSyncBits; // lane 0 too: its full pass is round 1
+        bool need = true;
+        for (int round = 0; round < 34; round++) {
+          uint32_t tp, tf, to, tr = 0;
+          if (lit_only) decode_ranges_lit<false>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u);
+          else decode_ranges<false>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, need, start, e_i, tp, tf, to, tr,
+                                    nullptr, 0u, nullptr);
+          if (need) { p = tp; flag = tf; n_out = to; n_rec = tr; }
+          const uint32_t pp = __shfl_up_sync(kFull, p, 1);
+          const uint32_t pf = __shfl_up_sync(kFull, flag, 1);
+          const uint32_t ns = lane == 0 ? b0 : (pf == P_OK ? pp : start);
+          need = ns != start;
+          start = ns;
+          if (lane == 0) atomicAdd(&j.counters[5], 1u); // instrumentation: decode rounds
+          if (!__any_sync(kFull, need)) break;
+        }
+        // the chain is valid up to the first lane that does not hand over: it must have met EOB -- or every lane
+        // hands over and the block goes on behind the window
+        const unsigned notok = __ballot_sync(kFull, flag != P_OK);
+        int f = 31;
+        if (notok == 0) {
+          if (wend >= bend) { bail = true; break; } // no EOB before the end of the input
+        } else {
+          f = __ffs(notok) - 1;
+          if (__shfl_sync(kFull, flag, f) != P_EOB) { bail = true; break; }
+        }
+        const bool mine = lane <= f;
+        uint32_t xo = mine ? n_out : 0u, xr = mine ? n_rec : 0u;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t yo = __shfl_up_sync(kFull, xo, o), yr = __shfl_up_sync(kFull, xr, o);
+          if (lane >= o) { xo += yo; xr += yr; }
+        }
+        const uint32_t tot_o = __shfl_sync(kFull, xo, 31), tot_r = __shfl_sync(kFull, xr, 31);
+        if (tot_o > cap - opos || tot_r > rec_cap - nrec) { bail = true; break; }
+        {
+          uint32_t tp, tf, to, tr = 0;
+          if (lit_only)
+            decode_ranges_lit<true>(sm, in, cur_len, bend, mine, start, e_i, tp, tf, to, out,
+                                    opos + xo - (mine ? n_out : 0u));
+          else
+            decode_ranges<true>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, mine, start, e_i, tp, tf, to, tr, out,
+                                opos + xo - (mine ? n_out : 0u), rec + nrec + xr - (mine ? n_rec : 0u));
+          const bool bad = mine && (tf == P_BAD || tp != p || to != n_out || tr != n_rec);
+          if (__any_sync(kFull, bad)) { bail = true; break; }
+        }
+        opos += tot_o;
+        nrec += tot_r;
+        const uint32_t pend = __shfl_sync(kFull, p, f);
+#ifdef FB_INFLATE_DEBUG
+        if (lane == 0 && opos > 102800000u) printf("  win: b0=%u wend=%u bend=%u f=%d notok=%08x tot_o=%u pend=%u\n", b0, wend, bend, f, notok, tot_o, pend);
+#endif
+        if (notok == 0) {
+          if (pend <= b0 || pend >= bend) { bail = true; break; } // (no progress cannot happen: ranges are >= 256 bits)
+          b0 = pend; // the block goes on behind the window
+        } else {
+          eob = pend;
+          have_eob = true;
+        }
       }
+      if (bail) break;
       if (lane == 0) atomicAdd(&j.counters[6], 1u); // instrumentation: blocks
-      // the chain is valid up to the first lane that does not hand over; it must have met EOB
-      const unsigned notok = __ballot_sync(kFull, flag != P_OK);
-      if (notok == 0) { bail = true; break; } // no EOB before the end of the input
-      const int f = __ffs(notok) - 1;
-      if (__shfl_sync(kFull, flag, f) != P_EOB) { bail = true; break; }
-      const bool mine = lane <= f;
-      uint32_t xo = mine ? n_out : 0u, xr = mine ? n_rec : 0u;
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t yo = __shfl_up_sync(kFull, xo, o), yr = __shfl_up_sync(kFull, xr, o);
-        if (lane >= o) { xo += yo; xr += yr; }
-      }
-      const uint32_t tot_o = __shfl_sync(kFull, xo, 31), tot_r = __shfl_sync(kFull, xr, 31);
-      if (tot_o > cap - opos || tot_r > rec_cap - nrec) { bail = true; break; }
       {
-        uint32_t tp, tf, to, tr = 0;
-        if (lit_only)
-          decode_ranges_lit<true>(sm, in, cur_len, bend, mine, start, e_i, tp, tf, to, out,
-                                  opos + xo - (mine ? n_out : 0u));
-        else
-          decode_ranges<true>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, mine, start, e_i, tp, tf, to, tr, out,
-                              opos + xo - (mine ? n_out : 0u), rec + nrec + xr - (mine ? n_rec : 0u));
-        const bool bad = mine && (tf == P_BAD || tp != p || to != n_out || tr != n_rec);
-        if (__any_sync(kFull, bad)) { bail = true; break; }
+        const uint64_t w = ((uint64_t)(eob - blk_first_bit) * 5u) >> 2;
+        win_bits = w < 32u * kMinRange ? 32u * kMinRange : (w > 0x7fffffffull ? 0x7fffffffu : (uint32_t)w);
+        if (j.window_bits == 0xffffffffu) win_bits = 0xffffffffu; // experiment switch: no windows
       }
-      opos += tot_o;
-      nrec += tot_r;
       // continue after the EOB: re-base the uniform reader there
-      const uint32_t eob = __shfl_sync(kFull, p, f);
       if ((int64_t)eob > cur_len * 8) { bail = true; break; }
       in += eob >> 3;
       cur_len -= (int64_t)(eob >> 3);
@@ -711,9 +749,19 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
 
 } // namespace par
 
-void launch_inflate3(const InflateJob &j, int num_sms, cudaStream_t st)
+void launch_inflate3(const InflateJob &j_in, int num_sms, cudaStream_t st)
 {
-  if (j.nstreams == 0) return;
+  if (j_in.nstreams == 0) return;
+  InflateJob j = j_in;
+  {
+    static long win_kb = -2;
+    if (win_kb == -2) {
+      const char *e = getenv("FB200_INFLATE_WINDOW_KB"); // first-block window; 0 = no windows at all
+      win_kb = e ? atol(e) : -1;
+    }
+    if (win_kb == 0) j.window_bits = 0xffffffffu;
+    else if (win_kb > 0) j.window_bits = (uint32_t)(win_kb * 8192);
+  }
   static int minb = 0;
   if (!minb) {
     const char *e = getenv("FB200_INFLATE_CTAS");

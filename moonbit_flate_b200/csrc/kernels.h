@@ -44,13 +44,39 @@ struct DeflateJob {
 };
 constexpr int kFreqStride = 320;
 
+// Block-parallel parse of multi-block streams.  The blocks of one stream are chained only through the hash
+// table (what the previous block left within 32768 bytes of its end), so all blocks are parsed at once from a
+// guessed table (empty in round 1) and a block is parsed again whenever the end table of its predecessor has
+// changed; block 0 is exact after round 1, and the fixpoint -- no end table changed -- is the sequential result.
+// Text needs about 5 rounds whatever the number of blocks.  All pointers are device pointers.
+struct BlockParJob {
+  const uint32_t *list;    // blocks to parse in this round (global block indices)
+  uint32_t nlist;
+  const uint64_t *mb_idx;  // [nblocks + 1] index of a block among the blocks of multi-block streams
+  uint16_t *tabs;          // [2][nmb][1 << 14] normalised end tables (distance from the block end, 0 = none in reach)
+  uint64_t nmb;
+  const uint8_t *lat_prev; // [nmb] which of the two copies is a block's latest end table (before this round)
+  uint8_t *lat_next;       // [nmb]
+  uint8_t *chg_next;       // [nmb] the block's end table changed in this round
+  int round;
+};
+
 // one-time device tables (probe schedule); call once per context
 void launch_init_tables(cudaStream_t st);
 // setup: per-stream block counts -> stream_blk0 (scan) ; then per-block stream ids
 void launch_count_blocks(const DeflateJob &j, cudaStream_t st);
+void launch_count_multi(const DeflateJob &j, cudaStream_t st);
 void launch_fill_blocks(const DeflateJob &j, cudaStream_t st);
 // K1: greedy LZ77 parse, one warp per stream (deflate-fast.mbt:123-342)
 void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st);
+// the two halves of launch_parse: streams with one parsed block / streams with several (sequential per stream)
+void launch_parse_single(const DeflateJob &j, int num_sms, cudaStream_t st);
+void launch_parse_multi(const DeflateJob &j, int num_sms, cudaStream_t st);
+// block-parallel rounds for the multi-block streams (see BlockParJob)
+void launch_bp_flags(const DeflateJob &j, uint64_t *flags, cudaStream_t st);
+void launch_bp_round(const DeflateJob &j, const BlockParJob &bp, const uint8_t *chg_prev, uint32_t *list, uint32_t *nlist,
+                     cudaStream_t st);
+void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *counter, int num_sms, cudaStream_t st);
 // FB200_PARSE_L2PERSIST=1 only: to be called once the parse has completed (un-pins its L2 lines); returns at once otherwise
 void parse_release_l2();
 bool parse_uses_l2_persistence();
@@ -108,6 +134,7 @@ struct InflateJob {
   const uint64_t *rec_off;  // [nstreams+1] record area of each stream
   uint32_t *nrec;           // [nstreams] records written (0: nothing to copy, or stream handed to the exact kernel)
   const uint32_t *order;    // [nstreams] decode order (largest compressed size first)
+  uint32_t window_bits;     // inflate3: speculation window of a stream's first block (0: the library's default)
 };
 // K6: batched inflate.  fast_v1: warp-per-stream fast kernel (inflate.cu); otherwise the caller has run
 // launch_inflate2 and only the exact kernel runs here, over the fallback list.

@@ -103,7 +103,8 @@ __device__ __forceinline__ int match_tail(const uint8_t *srcb, int s2, int t, in
 }
 
 template <bool MULTI, typename T, bool GTAB>
-__device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table, uint8_t *scratch, int wide)
+__device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table, uint8_t *scratch, int wide,
+                                             const BlockParJob *bp = nullptr)
 {
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1;
@@ -113,6 +114,12 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
     uint32_t st32 = 0;
     if (lane == 0) st32 = atomicAdd(counter, 1u);
     st32 = __shfl_sync(kFull, st32, 0);
+    uint64_t bp_gb = 0; // block-parallel rounds: the work item is one block of a multi-block stream
+    if (MULTI && bp) {
+      if (st32 >= bp->nlist) break;
+      bp_gb = bp->list[st32];
+      st32 = j.blk_stream[bp_gb];
+    }
     if (st32 >= j.nstreams) break;
     if (j.avail) { // host-buffer call: wait until the H2D stream has delivered this stream's bytes
       if (lane == 0)
@@ -125,40 +132,52 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
     if (is_multi != MULTI) continue;
     if (L < 128) continue; // nothing to parse: at most one small block
 
-    // DeflateFast::new (:111-117): empty table
-    {
+    const uint64_t blk0 = j.stream_blk0[st32];
+    const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
+    const uint32_t bp_b = (MULTI && bp) ? (uint32_t)(bp_gb - blk0) : 0u;
+    const bool bp_seed = MULTI && bp && bp->round > 1 && bp_b > 0 && !block_resets_table(bp_b); // round 1: empty tables
+    if (!bp_seed) { // DeflateFast::new (:111-117): empty table
       const uint32_t fill = MULTI ? 0u : 0xffffffffu;
       uint4 *t4 = reinterpret_cast<uint4 *>(table);
       const int n4 = (int)(kTableSize * sizeof(T) / 16);
       for (int i = lane; i < n4; i += 32) t4[i] = make_uint4(fill, fill, fill, fill);
       __syncwarp();
+    } else if (MULTI) {
+      // block-parallel round: the table as the previous block left it, from that block's normalised end table
+      // (distance of the last position of every bucket from the block end, 1..32768, 0 = none in reach).
+      // Positions are kept relative to (block start - 32768): the entry is 32768 - distance + 1.
+      const uint64_t mp = bp->mb_idx[bp_gb - 1];
+      const uint16_t *seed = bp->tabs + ((size_t)bp->lat_prev[mp] * bp->nmb + mp) * kTableSize;
+      for (int i = lane; i < kTableSize; i += 32) {
+        const uint32_t d = seed[i];
+        table[i] = (T)(d ? (uint32_t)kMaxMatchOffset - d + 1u : 0u);
+      }
+      __syncwarp();
     }
-
-    const uint64_t blk0 = j.stream_blk0[st32];
-    const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
     // DeflateFast.cur (:95-117): 65535 at the start, + the block length after every block.  When it reaches
     // buffer_reset (about every 2 GiB of one stream) encode calls shift_offsets (:129-132), which -- `prev` being
     // always empty, D1 -- clears the table and restarts cur at 32769 (:366-374).  Table positions are kept
     // relative to the last such point, so they neither wrap nor collide with the "empty" value.
     int64_t ref_cur = kBlockSize;
-    uint64_t pos_base = 0;
-    uint32_t b = 0;
-    for (; b < nblk; b++) {
+    int64_t pos_base = (MULTI && bp) ? (int64_t)bp_b * kBlockSize - kMaxMatchOffset : 0;
+    uint32_t b = bp_b;
+    const uint32_t b_end = (MULTI && bp) ? bp_b + 1 : nblk;
+    for (; b < b_end; b++) {
       const uint64_t boff = (uint64_t)b * kBlockSize;
       const int n = (int)((L - boff) < (uint64_t)kBlockSize ? (L - boff) : (uint64_t)kBlockSize);
       if (n < 128) break; // small tail: not parsed (deflate.mbt:244-257)
-      if (MULTI && ref_cur >= (int64_t)kBufferReset) {
+      if (MULTI && !bp && ref_cur >= (int64_t)kBufferReset) {
         uint4 *t4 = reinterpret_cast<uint4 *>(table);
         const int n4 = (int)(kTableSize * sizeof(T) / 16);
         for (int i = lane; i < n4; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
         ref_cur = kMaxMatchOffset + 1;
-        pos_base = boff;
+        pos_base = (int64_t)boff;
       }
       ref_cur += n;
       const uint8_t *srcb = j.src + o0 + boff;
       uint32_t *tok = j.tokens + o0 + boff;
-      const uint32_t S0 = (uint32_t)(boff - pos_base); // block start relative to the last table reset (MULTI)
+      const uint32_t S0 = (uint32_t)((int64_t)boff - pos_base); // block start relative to the last table reset (MULTI)
       const int s_limit = n - kInputMargin;
 
       int s = 0, next_emit = 0;
@@ -531,6 +550,29 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
       ntok += (uint32_t)(n - next_emit);
       if (lane == 0) j.blk_ntok[blk0 + b] = ntok;
       __syncwarp();
+      if (MULTI && bp && b + 1 < nblk && L - (uint64_t)(b + 1) * kBlockSize >= 128) {
+        // the next block is parsed too: leave it this block's end table, and note whether it differs from the
+        // one the previous round left (only then the next block has to be parsed again)
+        const uint64_t m = bp->mb_idx[bp_gb];
+        const uint32_t old_buf = bp->lat_prev[m], new_buf = old_buf ^ 1u;
+        const uint16_t *oldt = bp->tabs + ((size_t)old_buf * bp->nmb + m) * kTableSize;
+        uint16_t *newt = bp->tabs + ((size_t)new_buf * bp->nmb + m) * kTableSize;
+        const uint32_t end_rel = S0 + (uint32_t)n; // block end, relative like the table positions
+        bool diff = false;
+        for (int i = lane; i < kTableSize; i += 32) {
+          const uint32_t e = (uint32_t)table[i];
+          uint32_t d = e ? end_rel - (e - 1u) : 0u;
+          if (d > (uint32_t)kMaxMatchOffset) d = 0;
+          diff |= (bp->round == 1) || (oldt[i] != (uint16_t)d);
+          newt[i] = (uint16_t)d;
+        }
+        diff = __any_sync(kFull, diff);
+        if (lane == 0) {
+          bp->lat_next[m] = (uint8_t)new_buf;
+          bp->chg_next[m] = diff ? 1 : 0;
+        }
+        __syncwarp();
+      }
     }
   }
 }
@@ -555,6 +597,56 @@ __global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *g
   }
 }
 
+// One round of the block-parallel parse of multi-block streams: the blocks on the list are parsed, each from the
+// end table its predecessor has at the moment.
+__global__ void k_parse_blocks(DeflateJob j, BlockParJob bp, uint32_t *counter, int smem_warps, void *gtables)
+{
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  if (warp < smem_warps) {
+    parse_worker<true, uint32_t, false>(j, counter, reinterpret_cast<uint32_t *>(smem_raw) + (size_t)warp * kTableSize, nullptr, 0, &bp);
+  } else {
+    const int gw = (int)(blockDim.x >> 5) - smem_warps;
+    uint32_t *table = reinterpret_cast<uint32_t *>(gtables) + ((size_t)blockIdx.x * gw + (warp - smem_warps)) * kTableSize;
+    parse_worker<true, uint32_t, true>(j, counter, table, nullptr, 0, &bp);
+  }
+}
+
+__device__ __forceinline__ bool blk_of_multi_stream(const DeflateJob &j, uint64_t gb, uint32_t *b_out, bool *parsed)
+{
+  const uint32_t st = j.blk_stream[gb];
+  const uint64_t L = j.stream_off[st + 1] - j.stream_off[st];
+  const uint64_t b = gb - j.stream_blk0[st];
+  *b_out = (uint32_t)b;
+  *parsed = L - b * (uint64_t)kBlockSize >= 128;
+  return L >= (uint64_t)kBlockSize + 128;
+}
+
+__global__ void k_bp_flags(DeflateJob j, uint64_t *flags)
+{
+  const uint64_t gb = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb >= j.nblocks) return;
+  uint32_t b;
+  bool parsed;
+  flags[gb] = blk_of_multi_stream(j, gb, &b, &parsed) ? 1 : 0;
+}
+
+// Work list of a round: every parsed block in round 1, afterwards the blocks whose predecessor's end table
+// changed in the previous round.  Also carries the per-block state over to this round's arrays.
+__global__ void k_bp_round(DeflateJob j, BlockParJob bp, const uint8_t *chg_prev, uint32_t *list, uint32_t *nlist)
+{
+  const uint64_t gb = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb >= j.nblocks) return;
+  uint32_t b;
+  bool parsed;
+  if (!blk_of_multi_stream(j, gb, &b, &parsed)) return;
+  const uint64_t m = bp.mb_idx[gb];
+  bp.lat_next[m] = bp.round == 1 ? 0 : bp.lat_prev[m];
+  bp.chg_next[m] = 0;
+  const bool need = parsed && (bp.round == 1 || (b > 0 && !block_resets_table(b) && chg_prev[m - 1]));
+  if (need) list[atomicAdd(nlist, 1u)] = (uint32_t)gb;
+}
+
 void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
 
 // FB200_PARSE_WIDE=1 (in a build with -DFB_WIDE_BATCH=1) enables the 64-position batches of the global-table
@@ -574,7 +666,7 @@ void parse_release_l2()
   if (g_parse_persist > 0) cudaCtxResetPersistingL2Cache();
 }
 
-void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
+static void parse_init(int num_sms)
 {
   static bool inited = false;
   if (!inited) {
@@ -597,9 +689,9 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
                          g_parse_occ_single * kTableSize * 2 + gw * (g_parse_wide ? kWideScratch : 0));
     cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0));
+    cudaFuncSetAttribute(k_parse_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, g_parse_occ_multi * kTableSize * 4);
     inited = true;
   }
-  const int gw = g_parse_gwarps;
   {
     // Shared-memory carve-out: by default the smallest one that holds the tables (5 tables -> 164 KB, 92 KB of
     // L1).  Measured with 5 + 25 warps: 196 KB carve-out 19.8 ms per GiB, 228 KB 30.7 ms, default 18.6 ms.
@@ -613,6 +705,12 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
       }
     }
   }
+}
+
+void launch_parse_single(const DeflateJob &j, int num_sms, cudaStream_t st)
+{
+  parse_init(num_sms);
+  const int gw = g_parse_gwarps;
   // keep the global-memory tables resident in L2 (they are hit at random, 2 bytes at a time) while the
   // source and the token stream flow through
   int &persist = g_parse_persist;
@@ -644,13 +742,46 @@ void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
   }
   k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * 2 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
       j, j.counters + 0, g_parse_occ_single, g_parse_gtables, g_parse_wide);
-  k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
-      j, j.counters + 1, g_parse_occ_multi, g_parse_gtables, g_parse_wide);
   if (persist && gw) {
     cudaStreamAttrValue av{};
     av.accessPolicyWindow.num_bytes = 0;
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
   }
+}
+
+void launch_parse_multi(const DeflateJob &j, int num_sms, cudaStream_t st)
+{
+  parse_init(num_sms);
+  const int gw = g_parse_gwarps;
+  k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
+      j, j.counters + 1, g_parse_occ_multi, g_parse_gtables, g_parse_wide);
+}
+
+void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
+{
+  launch_parse_single(j, num_sms, st);
+  launch_parse_multi(j, num_sms, st);
+}
+
+void launch_bp_flags(const DeflateJob &j, uint64_t *flags, cudaStream_t st)
+{
+  if (j.nblocks == 0) return;
+  k_bp_flags<<<(unsigned)((j.nblocks + 255) / 256), 256, 0, st>>>(j, flags);
+}
+
+void launch_bp_round(const DeflateJob &j, const BlockParJob &bp, const uint8_t *chg_prev, uint32_t *list, uint32_t *nlist,
+                     cudaStream_t st)
+{
+  if (j.nblocks == 0) return;
+  k_bp_round<<<(unsigned)((j.nblocks + 255) / 256), 256, 0, st>>>(j, bp, chg_prev, list, nlist);
+}
+
+void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *counter, int num_sms, cudaStream_t st)
+{
+  parse_init(num_sms);
+  const int gw = g_parse_gwarps;
+  k_parse_blocks<<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4, st>>>(
+      j, bp, counter, g_parse_occ_multi, g_parse_gtables);
 }
 
 // ------------------------------------------------------------------
@@ -662,6 +793,26 @@ __global__ void k_count_blocks(DeflateJob j, uint64_t *nblk_out)
   if (i >= j.nstreams) return;
   uint64_t L = j.stream_off[i + 1] - j.stream_off[i];
   nblk_out[i] = (L + kBlockSize - 1) / kBlockSize; // Compressor::write cuts at 65535 (deflate.mbt:222-229,:238)
+}
+
+// streams of more than one parsed block -> counters[12], their blocks -> counters[13] (saturating)
+__global__ void k_count_multi(DeflateJob j)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.nstreams) return;
+  const uint64_t L = j.stream_off[i + 1] - j.stream_off[i];
+  if (L >= (uint64_t)kBlockSize + 128) {
+    atomicAdd(&j.counters[12], 1u);
+    const uint64_t nb = (L + kBlockSize - 1) / kBlockSize;
+    const uint32_t old = atomicAdd(&j.counters[13], (uint32_t)(nb > 0x3fffffffu ? 0x3fffffffu : nb));
+    if (old > 0x7fffffffu) atomicExch(&j.counters[13], 0x7fffffffu);
+  }
+}
+
+void launch_count_multi(const DeflateJob &j, cudaStream_t st)
+{
+  if (j.nstreams == 0) return;
+  k_count_multi<<<(unsigned)((j.nstreams + 255) / 256), 256, 0, st>>>(j);
 }
 
 void launch_count_blocks(const DeflateJob &j, cudaStream_t st)
@@ -784,7 +935,11 @@ void preload_parse_kernels()
   cudaFuncGetAttributes(&a, k_init_sched);
   cudaFuncGetAttributes(&a, k_parse<false>);
   cudaFuncGetAttributes(&a, k_parse<true>);
+  cudaFuncGetAttributes(&a, k_parse_blocks);
+  cudaFuncGetAttributes(&a, k_bp_flags);
+  cudaFuncGetAttributes(&a, k_bp_round);
   cudaFuncGetAttributes(&a, k_count_blocks);
+  cudaFuncGetAttributes(&a, k_count_multi);
   cudaFuncGetAttributes(&a, k_fill_blocks);
   cudaFuncGetAttributes(&a, k_fill_seg_off);
   cudaFuncGetAttributes(&a, k_affine_u64);

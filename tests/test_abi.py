@@ -67,3 +67,25 @@ def test_product_never_references_the_oracle():
                 assert "flate_oracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)
     inc = open(os.path.join(ROOT, "include", "flate_b200.h")).read()
     assert "flate_oracle" not in inc
+
+
+def test_table_reset_blocks_closed_form():
+    """deflate-fast.mbt:129-132 / :366-374: encode clears the table when cur >= buffer_reset.  cur is 65535 before
+    block 0 and grows by 65535 per full block; after a reset it restarts at 32769.  The parse uses a closed form for
+    the reset blocks (common.cuh block_resets_table): compare it with the running sum over 200000 blocks."""
+    import ctypes as C
+    import moonbit_flate_b200 as fb
+    f = fb._lib.fb200_debug_block_resets
+    f.restype = C.c_int
+    f.argtypes = [C.c_uint64]
+    buffer_reset = 2147483647 - 2 * 65535
+    cur = 65535
+    resets = []
+    for b in range(200000):
+        if cur >= buffer_reset:
+            resets.append(b)
+            cur = 32768 + 1
+        cur += 65535
+    assert resets[:3] == [32766, 65532, 98298]
+    got = [b for b in range(200000) if f(b)]
+    assert got == resets

@@ -365,7 +365,7 @@ def test_stream_beyond_2gib_table_reset(ctx, oracle, corpus):
     DeflateFast.cur reaches buffer_reset and shift_offsets clears the hash table (prev is always empty, D1), so
     the block that follows finds no 4-byte matches into its predecessor.  The GPU stream must equal the
     oracle's byte for byte (the oracle restates shift_offsets), and inflate back."""
-    nblk = 32770  # the reset happens at the start of block 32767
+    nblk = 32770  # the reset happens at the start of block 32766
     n = nblk * 65535 + 777
     src = corpus.fill((n + 65535) // 65536, 65536, seed=77, klass=Corpus.TEXT)[:n]
     off = np.array([0, n], dtype=np.uint64)
@@ -377,3 +377,27 @@ def test_stream_beyond_2gib_table_reset(ctx, oracle, corpus):
     out, olen, st, eo, cons = ctx.inflate_batch(comp, doff, off)
     assert int(st[0]) == 0 and int(olen[0]) == n and int(cons[0]) == comp.size
     assert np.array_equal(out, src)
+
+
+def test_inflate_long_codes_next_to_short_ones(ctx, oracle):
+    """Literal-heavy data whose Huffman code reaches 13-15 bits for rare bytes: a rare byte followed by two common
+    ones puts three literals into one 32-bit peek of the parallel decoder only if the first two codes leave room
+    for the third look-up (regression: the third literal used to be read past the peek)."""
+    rng = np.random.default_rng(77)
+    datas = []
+    for k in range(24):
+        ratio = 0.80 + 0.008 * k  # geometric byte frequencies: code lengths from 2-3 bits up to 15
+        p = ratio ** np.arange(256)
+        p /= p.sum()
+        perm = rng.permutation(256)
+        n = 60000 + 211 * k
+        datas.append(perm[rng.choice(256, size=n, p=p)].astype(np.uint8).tobytes())
+    src = np.frombuffer(b"".join(datas), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(d) for d in datas])]).astype(np.uint64)
+    comp, doff = ctx.deflate_streams(src, off)
+    for i, d in enumerate(datas):
+        assert comp[int(doff[i]): int(doff[i + 1])].tobytes() == oracle.deflate(d), i
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, doff, off)
+    assert (st == 0).all() and np.array_equal(olen, np.diff(off))
+    assert np.array_equal(out, src)
+    assert int(ctx.last_stats().inflate_fallbacks) == 0
