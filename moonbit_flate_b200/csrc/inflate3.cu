@@ -689,7 +689,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
 #endif
         if (notok == 0) {
           if (pend <= b0 || pend >= bend) { bail = true; break; } // (no progress cannot happen: ranges are >= 256 bits)
-          b0 = pend; // the block goes on behind the window
+          b0 = pend; // the block goes on behind the window, which doubles: the guess was too small
+          if (win_bits < 0x40000000u) win_bits *= 2u;
         } else {
           eob = pend;
           have_eob = true;
@@ -699,7 +700,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
       if (lane == 0) atomicAdd(&j.counters[6], 1u); // instrumentation: blocks
       {
         const uint64_t w = ((uint64_t)(eob - blk_first_bit) * 5u) >> 2;
-        win_bits = w < 32u * kMinRange ? 32u * kMinRange : (w > 0x7fffffffull ? 0x7fffffffu : (uint32_t)w);
+        const uint32_t wmin = 24u * 1024u * 8u; // a tiny block (a run of zeros) says little about the next one
+        win_bits = w < wmin ? wmin : (w > 0x7fffffffull ? 0x7fffffffu : (uint32_t)w);
         if (j.window_bits == 0xffffffffu) win_bits = 0xffffffffu; // experiment switch: no windows
       }
       // continue after the EOB: re-base the uniform reader there
