@@ -163,3 +163,23 @@ def test_batched_parse_model_fuzz(hm, oracle):
         toks, ntok = hm.parse_stream(d, v2=True)
         assert list(ntok) == list(wntok), (i, len(d))
         assert np.array_equal(toks, wtok), (i, len(d))
+
+
+@pytest.mark.parametrize("klass,nblk", [(0, 40), (1, 40), (2, 12), (3, 40), (-1, 60)])
+def test_block_parallel_parse_fixpoint(klass, nblk):
+    """CPU model of the block-parallel parse of multi-block streams (tests/hostmodel/blockpar_model.c, on the
+    oracle's own encode): parse every block from an empty table, then re-parse the blocks whose predecessor's
+    normalised end table changed, until nothing changes; the tokens of every block then equal the sequential
+    parse's, and the fixpoint is reached in a handful of rounds whatever the number of blocks."""
+    import ctypes as C
+    so = os.path.join(ROOT, "tests", "hostmodel", "libfb_blockpar.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostmodel"), "libfb_blockpar.so"])
+    L = C.CDLL(so)
+    L.fbm_blockpar_check.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_long)]
+    n = nblk * 65535
+    src = Corpus().fill((n + 65535) // 65536, 65536, seed=5, klass=klass)[:n]
+    rounds, parses = C.c_int(), C.c_long()
+    assert L.fbm_blockpar_check(src.ctypes.data, nblk, C.byref(rounds), C.byref(parses)) == 1
+    assert rounds.value <= 10, rounds.value
+    assert parses.value <= 6 * nblk, parses.value
