@@ -172,7 +172,10 @@ void launch_layout(const DeflateJob &j, cudaStream_t st)
 // ------------------------------------------------------------------
 // K4: bit packing, one CTA per block.
 constexpr int kPackThreads = 256;
-constexpr int kItemsPerThread = 4;
+#ifndef FB_PACK_ITEMS
+#define FB_PACK_ITEMS 8 // measured: 4 -> 2.40 ms per GiB, 6 -> 2.24, 8 -> 2.12, 12 -> 2.71, 16 -> 2.66
+#endif
+constexpr int kItemsPerThread = FB_PACK_ITEMS;
 constexpr int kChunkItems = kPackThreads * kItemsPerThread;
 constexpr int kStageWords = kChunkItems * 48 / 32 + 4;
 
@@ -184,14 +187,15 @@ __device__ __forceinline__ void or_byte(uint32_t *dst32, uint64_t byte_pos, uint
 __device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t bitoff, uint64_t val, int nb)
 {
   if (nb == 0) return;
+  // the (at most 48) bits land in up to three words: 32-bit funnel shifts instead of 64-bit ones
   const uint32_t w = bitoff >> 5, sh = bitoff & 31;
-  const uint32_t lo = (uint32_t)(val << sh);
-  if (lo) atomicOr(&stage[w], lo);
-  const uint64_t rest = sh ? (val >> (32 - sh)) : (val >> 32);
-  if (rest) {
-    atomicOr(&stage[w + 1], (uint32_t)rest);
-    if (rest >> 32) atomicOr(&stage[w + 2], (uint32_t)(rest >> 32));
-  }
+  const uint32_t vlo = (uint32_t)val, vhi = (uint32_t)(val >> 32);
+  const uint32_t a = vlo << sh;
+  const uint32_t b = __funnelshift_l(vlo, vhi, sh);
+  const uint32_t c = __funnelshift_l(vhi, 0u, sh);
+  if (a) atomicOr(&stage[w], a);
+  if (b) atomicOr(&stage[w + 1], b);
+  if (c) atomicOr(&stage[w + 2], c);
 }
 
 __global__ void __launch_bounds__(kPackThreads) k_pack(DeflateJob j)
