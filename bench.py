@@ -410,13 +410,16 @@ def main():
 
         cl = e2e_step()
         assert int(h_status.abs().sum()) == 0 and torch.equal(h_out, h_src), "e2e round trip mismatch"
-        ksteps = max(1, min(args.steps, 3))
+        ksteps = max(1, min(args.steps, 10))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        per_step = []
         t0 = time.perf_counter()
         for _ in range(ksteps):
+            ts = time.perf_counter()
             cl = e2e_step()
+            per_step.append(time.perf_counter() - ts)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / ksteps
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -427,6 +430,7 @@ def main():
                "h2d_bytes_per_step": int((nbytes + cl + 3 * meta) * world),
                "d2h_bytes_per_step": int((cl + nbytes + meta + nseg * 20) * world),
                "steps": ksteps, "ms_per_step": round(float(t_e.item()) * 1e3, 3),
+               "ms_per_step_min_max_rank0": [round(min(per_step) * 1e3, 3), round(max(per_step) * 1e3, 3)],
                "path": "fb200_deflate_segments + fb200_inflate_batch with pinned host buffers"}
 
     if rank != 0:

@@ -401,3 +401,28 @@ def test_inflate_long_codes_next_to_short_ones(ctx, oracle):
     assert (st == 0).all() and np.array_equal(olen, np.diff(off))
     assert np.array_equal(out, src)
     assert int(ctx.last_stats().inflate_fallbacks) == 0
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_multi_block_streams_both_parse_paths(oracle, corpus, monkeypatch, mode):
+    """Multi-block streams are parsed either by one warp per stream (FB200_PARSE_BLOCKPAR=0) or block-parallel by
+    fixpoint rounds (=2; the default picks by the number of such streams): both must give the oracle's bytes,
+    for streams whose last block is parsed, stored (< 17 bytes), literal-only (< 128) or missing."""
+    import moonbit_flate_b200 as fb
+
+    monkeypatch.setenv("FB200_PARSE_BLOCKPAR", mode)
+    c = fb.Context()
+    monkeypatch.delenv("FB200_PARSE_BLOCKPAR")
+    try:
+        sizes = [65535 + 128, 2 * 65535, 2 * 65535 + 5, 2 * 65535 + 100, 3 * 65535 + 4000, 700000, 65536, 1000, 0,
+                 5 * 65535 + 127, 5 * 65535 + 128]
+        datas = [corpus.unit(n, seed=61, index=i, klass=(0, 1, 3, 5, 0, -1, 0, 0, 0, 1, 2)[i]) for i, n in enumerate(sizes)]
+        src = np.frombuffer(b"".join(datas), dtype=np.uint8)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        comp, doff = c.deflate_streams(src, off)
+        for i, d in enumerate(datas):
+            assert comp[int(doff[i]): int(doff[i + 1])].tobytes() == oracle.deflate(d), (mode, i, sizes[i])
+        out, olen, st, eo, cons = c.inflate_batch(comp, doff, off)
+        assert (st == 0).all() and np.array_equal(out, src)
+    finally:
+        c.close()
