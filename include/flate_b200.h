@@ -111,6 +111,12 @@ int fb200_deflate_segments_dev(fb200_ctx *ctx, const uint8_t *d_src, uint64_t n,
 int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const uint64_t *comp_off, uint64_t nstreams,
                         uint8_t *out, const uint64_t *out_off, uint64_t *out_len, int32_t *status,
                         int64_t *err_off, uint64_t *consumed);
+/* One stream decoded with a preset dictionary (&Reader::new_dict, inflate.mbt:310-317; DictDecoder::new,
+ * dict-decoder.mbt:42-60): as if the uncompressed data started with dict, which has already been read.  Host
+ * buffers; consumed may be NULL. */
+int fb200_inflate_dict(fb200_ctx *ctx, const uint8_t *comp, uint64_t n, const uint8_t *dict, uint64_t dict_len,
+                       uint8_t *out, uint64_t cap, uint64_t *out_len, int32_t *status, int64_t *err_off,
+                       uint64_t *consumed);
 /* Device-buffer variant: every pointer is a device pointer (consumed may be NULL). */
 int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t *d_comp_off,
                             uint64_t nstreams, uint8_t *d_out, const uint64_t *d_out_off, uint64_t *d_out_len,
@@ -162,6 +168,13 @@ void fb200_writer_free(fb200_writer *w);
 typedef struct fb200_reader fb200_reader;
 /* &Reader::new (inflate.mbt:305): comp must stay valid until the first read. */
 fb200_reader *fb200_reader_new(fb200_ctx *ctx, const uint8_t *comp, uint64_t n);
+/* &Reader::new_dict (inflate.mbt:310-317): the stream is decoded as if the uncompressed data started with
+ * dict, which has already been read (only its last 32768 bytes matter, dict-decoder.mbt:49-52). */
+fb200_reader *fb200_reader_new_dict(fb200_ctx *ctx, const uint8_t *comp, uint64_t n, const uint8_t *dict,
+                                    uint64_t dict_len);
+/* Decompressor::reset(r, dict) / make_reader (inflate.mbt:857-883): a new input (and dictionary, may be
+ * NULL / 0) for an existing object; everything buffered is dropped. */
+int fb200_reader_reset(fb200_reader *r, const uint8_t *comp, uint64_t n, const uint8_t *dict, uint64_t dict_len);
 /* impl @io.Reader for Decompressor (inflate.mbt:382-407).  Returns the byte
  * count; *status = -1 while the reference returns (n, None), otherwise the
  * FB200_ST_* code delivered together with the last bytes. */

@@ -87,7 +87,11 @@ ABI = {
     "fb200_writer_write": (C.c_int64, [C.c_void_p, _u8p, C.c_uint64]),
     "fb200_writer_close": (C.c_int, [C.c_void_p]),
     "fb200_writer_free": (None, [C.c_void_p]),
+    "fb200_inflate_dict": (C.c_int, [C.c_void_p, _u8p, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_uint64, _u64p, C.c_void_p,
+                                     C.c_void_p, _u64p]),
     "fb200_reader_new": (C.c_void_p, [C.c_void_p, _u8p, C.c_uint64]),
+    "fb200_reader_new_dict": (C.c_void_p, [C.c_void_p, _u8p, C.c_uint64, _u8p, C.c_uint64]),
+    "fb200_reader_reset": (C.c_int, [C.c_void_p, _u8p, C.c_uint64, _u8p, C.c_uint64]),
     "fb200_reader_read": (C.c_uint64, [C.c_void_p, _u8p, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "fb200_reader_close": (C.c_int, [C.c_void_p]),
     "fb200_reader_free": (None, [C.c_void_p]),
@@ -370,18 +374,37 @@ class Reader:
     32 KiB window flush per call, ``err`` is ``None`` until the stream ends and
     then ``IOEOF`` or the reference's error text."""
 
-    def __init__(self, comp, ctx: Optional[Context] = None):
+    def __init__(self, comp, ctx: Optional[Context] = None, _dict: Optional[bytes] = None):
         self._ctx = ctx or default_context()
         if hasattr(comp, "getvalue"):
             comp = comp.getvalue()
         self._comp = _as_u8(comp).copy()
-        self._h = _lib.fb200_reader_new(self._ctx._h, _ptr(self._comp), self._comp.size)
+        if _dict is None:
+            self._h = _lib.fb200_reader_new(self._ctx._h, _ptr(self._comp), self._comp.size)
+        else:
+            d = _as_u8(_dict)
+            self._h = _lib.fb200_reader_new_dict(self._ctx._h, _ptr(self._comp), self._comp.size, _ptr(d), d.size)
         if not self._h:
             raise FlateError("fb200_reader_new failed")
 
     @classmethod
     def new(cls, comp, ctx: Optional[Context] = None) -> "Reader":
         return cls(comp, ctx)
+
+    @classmethod
+    def new_dict(cls, comp, dict_: bytes, ctx: Optional[Context] = None) -> "Reader":
+        """&Reader::new_dict (inflate.mbt:310-317): decode as if the output started with dict_ (already read)."""
+        return cls(comp, ctx, _dict=dict_)
+
+    def reset(self, comp, dict_: bytes = b""):
+        """Decompressor::reset(r, dict) (inflate.mbt:862-883): new input and dictionary, state dropped."""
+        if hasattr(comp, "getvalue"):
+            comp = comp.getvalue()
+        self._comp = _as_u8(comp).copy()
+        d = _as_u8(dict_)
+        rc = _lib.fb200_reader_reset(self._h, _ptr(self._comp), self._comp.size, _ptr(d) if d.size else None, d.size)
+        if rc != OK:
+            raise FlateError(f"fb200_reader_reset failed ({rc})")
 
     def read(self, n: int):
         buf = np.empty(max(n, 1), np.uint8)

@@ -852,6 +852,7 @@ extern "C" int fb200_last_blocks(const fb200_ctx *cctx, uint32_t *blk_ntok, uint
 // inflate
 
 struct InflateHooks { // host-buffer calls only
+  const uint32_t *hist0 = nullptr; // preset dictionaries (device array), see InflateJob::hist0
   const uint32_t *avail = nullptr;
   uint32_t *group_done = nullptr;
   volatile uint32_t *group_flag = nullptr;
@@ -881,13 +882,14 @@ static int inflate_launch(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t 
   j.counters = ctx->counters.as<uint32_t>();
   j.fallback = ctx->i_fallback.as<uint32_t>();
   j.avail = hk.avail;
+  j.hist0 = hk.hist0;
   j.group_done = hk.group_done;
   j.group_flag = hk.group_flag;
   j.group_streams = hk.group_streams;
   for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
   uint64_t launches = nstreams ? 2 : 0;
   int mode = ctx->inflate_mode;
-  if (mode == 2 && hk.avail) mode = 3; // the overlapped host path is wired into modes 1 and 3
+  if (mode == 2 && (hk.avail || hk.hist0)) mode = 3; // the overlapped host path and dictionaries are wired into modes 1 and 3
   if (mode != 1 && nstreams) {
     // record areas: sized from the output capacity (a match yields >= 3 bytes)
     uint64_t cap_total = cap_total_known;
@@ -1151,6 +1153,7 @@ struct fb200_reader {
   fb200_ctx *ctx;
   const uint8_t *comp;
   uint64_t n;
+  std::vector<uint8_t> dict; // &Reader::new_dict / Decompressor::reset: the last <= 32768 bytes of the dictionary
   bool decoded = false;
   std::vector<uint8_t> out;
   uint64_t total = 0, pos = 0;
@@ -1170,9 +1173,82 @@ extern "C" fb200_reader *fb200_reader_new(fb200_ctx *ctx, const uint8_t *comp, u
   return r;
 }
 
+// One stream with a preset dictionary (&Reader::new_dict, inflate.mbt:310-317): the dictionary tail sits directly
+// in front of the output slot on the device (InflateJob::hist0), exactly like DictDecoder::new pre-loads the
+// window (dict-decoder.mbt:42-60).
+extern "C" int fb200_inflate_dict(fb200_ctx *ctx, const uint8_t *comp, uint64_t n, const uint8_t *dict, uint64_t dict_len,
+                                  uint8_t *out, uint64_t cap, uint64_t *out_len, int32_t *status, int64_t *err_off,
+                                  uint64_t *consumed)
+{
+  if (!ctx || (!comp && n) || (!dict && dict_len) || (!out && cap) || !out_len || !status || !err_off) return FB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (dict_len > (uint64_t)kMaxMatchOffset) { // only the last 32768 bytes matter (dict-decoder.mbt:49-52)
+    dict += dict_len - kMaxMatchOffset;
+    dict_len = kMaxMatchOffset;
+  }
+  const uint64_t D = dict_len;
+  const uint64_t Dpad = (D + 15) & ~15ull; // keep the slot 16-byte aligned
+  CK(ctx->p_in[1].ensure(n + 256));
+  CK(ctx->p_out[1].ensure(Dpad + cap + 16));
+  CK(ctx->p_off_in[1].ensure(64));
+  CK(ctx->p_off_out[1].ensure(64));
+  CK(ctx->p_len[1].ensure(64));
+  CK(ctx->p_status[1].ensure(64));
+  CK(ctx->p_eoff[1].ensure(64));
+  CK(ctx->p_cons[1].ensure(64));
+  uint8_t *d_out = ctx->p_out[1].as<uint8_t>();
+  uint64_t *h = ctx->pinned + 40; // staging of the small arrays
+  h[0] = 0; h[1] = n;                    // comp_off
+  h[2] = Dpad; h[3] = Dpad + cap;        // out_off
+  reinterpret_cast<uint32_t *>(h + 4)[0] = (uint32_t)D; // hist0
+  if (n) CK(cudaMemcpyAsync(ctx->p_in[1].p, comp, n, cudaMemcpyHostToDevice, s));
+  if (D) CK(cudaMemcpyAsync(d_out + Dpad - D, dict, D, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->p_off_in[1].p, h, 16, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->p_off_out[1].p, h + 2, 16, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->p_cons[1].as<uint8_t>() + 32, h + 4, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s)); // (comp / dict may be pageable: the staging must not be reused before they are read)
+  InflateHooks hk;
+  hk.hist0 = reinterpret_cast<const uint32_t *>(ctx->p_cons[1].as<uint8_t>() + 32);
+  int rc = inflate_launch(ctx, ctx->p_in[1].as<uint8_t>(), ctx->p_off_in[1].as<uint64_t>(), 1, d_out,
+                          ctx->p_off_out[1].as<uint64_t>(), ctx->p_len[1].as<uint64_t>(), ctx->p_status[1].as<int32_t>(),
+                          ctx->p_eoff[1].as<int64_t>(), ctx->p_cons[1].as<uint64_t>(), cap, hk);
+  if (rc != FB200_OK) return rc;
+  rc = inflate_finish(ctx);
+  if (rc != FB200_OK) return rc;
+  CK(cudaMemcpyAsync(h + 8, ctx->p_len[1].p, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h + 9, ctx->p_status[1].p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h + 10, ctx->p_eoff[1].p, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h + 11, ctx->p_cons[1].p, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *out_len = h[8];
+  *status = reinterpret_cast<int32_t *>(h + 9)[0];
+  *err_off = reinterpret_cast<int64_t *>(h + 10)[0];
+  if (consumed) *consumed = h[11];
+  if (*out_len) CK(cudaMemcpy(out, d_out + Dpad, *out_len, cudaMemcpyDeviceToHost));
+  return FB200_OK;
+}
+
 static void reader_decode(fb200_reader *r)
 {
   r->decoded = true;
+  if (!r->dict.empty()) {
+    uint64_t cap = r->n * 8 + 65536;
+    for (;;) {
+      r->out.resize(cap);
+      uint64_t olen = 0;
+      int32_t st = -1;
+      int64_t eo = 0;
+      r->rc = fb200_inflate_dict(r->ctx, r->comp, r->n, r->dict.data(), r->dict.size(), r->out.data(), cap, &olen, &st,
+                                 &eo, nullptr);
+      if (r->rc != FB200_OK) { r->status = FB200_ST_INTERNAL; r->total = 0; return; }
+      if (st == FB200_ST_DST_TOO_SMALL && cap < r->n * 1040 + 65536) { cap *= 4; continue; }
+      r->total = olen;
+      r->status = st;
+      r->err_off = eo;
+      return;
+    }
+  }
   uint64_t cap = r->n * 8 + 65536;
   for (;;) {
     r->out.resize(cap);
@@ -1187,6 +1263,40 @@ static void reader_decode(fb200_reader *r)
     r->err_off = eo;
     return;
   }
+}
+
+static void reader_set_dict(fb200_reader *r, const uint8_t *dict, uint64_t n)
+{
+  // DictDecoder::new keeps the last `size` (32768) bytes of the dictionary (dict-decoder.mbt:49-52)
+  if (n > (uint64_t)kMaxMatchOffset) {
+    dict += n - kMaxMatchOffset;
+    n = kMaxMatchOffset;
+  }
+  if (n) r->dict.assign(dict, dict + n);
+  else r->dict.clear();
+}
+
+extern "C" fb200_reader *fb200_reader_new_dict(fb200_ctx *ctx, const uint8_t *comp, uint64_t n, const uint8_t *dict,
+                                               uint64_t dict_len)
+{
+  if (!dict && dict_len) return nullptr;
+  fb200_reader *r = fb200_reader_new(ctx, comp, n);
+  if (r) reader_set_dict(r, dict, dict_len);
+  return r;
+}
+
+extern "C" int fb200_reader_reset(fb200_reader *r, const uint8_t *comp, uint64_t n, const uint8_t *dict, uint64_t dict_len)
+{
+  if (!r || (!comp && n) || (!dict && dict_len)) return FB200_ERR_ARG;
+  r->comp = comp;
+  r->n = n;
+  r->decoded = false;
+  r->total = r->pos = 0;
+  r->status = -1;
+  r->err_off = 0;
+  r->rc = FB200_OK;
+  reader_set_dict(r, dict, dict_len);
+  return FB200_OK;
 }
 
 extern "C" uint64_t fb200_reader_read(fb200_reader *r, uint8_t *buf, uint64_t n, int32_t *status, int64_t *err_off)

@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 10) k_inflate_fast(InflateJob
     FastBits fb;
     fb.init(in, in_len);
     uint32_t opos = 0;
+    const uint32_t h0 = j.hist0 ? j.hist0[st32] : 0u; // preset dictionary in front of the slot
     bool bail = in_len > 0x0fffffffull; // keep bit counts comfortably inside 32/64-bit ranges
     bool done = false;
     // deferred back-reference copy: byte loaded at one match, stored at the next (hides the L2 round trip)
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 10) k_inflate_fast(InflateJob
         if ((d >> 4) >= (uint32_t)kNumDist) { bail = true; break; }
         const uint32_t dt = c_dist_tab[d >> 4]; // distance base + extra bits (inflate.mbt:656-674)
         const uint32_t dist = (dt & 0xffffu) + fb.take((int)(dt >> 16));
-        if (dist > opos || length > cap - opos) { bail = true; break; }
+        if (dist > opos + h0 || length > cap - opos) { bail = true; break; }
         // retire the previous deferred copy, then make lane-0 literal stores visible to the copy loads
         if (pend_ptr) { *pend_ptr = (uint8_t)pend_val; pend_ptr = nullptr; }
         __syncwarp();
@@ -603,6 +604,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(InflateJob j)
     st32 = __shfl_sync(kFull, st32, 0);
     if (st32 >= nfallback) break;
     st32 = j.fallback[st32];
+    const uint64_t h0 = j.hist0 ? j.hist0[st32] : 0u; // preset dictionary in front of the slot
 
     BitReader br;
     br.in = j.comp + j.comp_off[st32];
@@ -801,8 +803,8 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_inflate(InflateJob j)
               br.consume(nb);
               dist = (1 << (nb + 1)) + 1 + extra;
             } else { status = FB200_ST_CORRUPT; err_off = (int64_t)br.roffset(); bev = EV_ERR; break; }
-            // dist > hist_size (:677): hist_size = min(bytes produced, 32768), dist <= 32768
-            if ((uint64_t)dist > opos) { status = FB200_ST_CORRUPT; err_off = (int64_t)br.roffset(); bev = EV_ERR; break; }
+            // dist > hist_size (:677): hist_size = min(dictionary + bytes produced, 32768), dist <= 32768
+            if ((uint64_t)dist > opos + h0) { status = FB200_ST_CORRUPT; err_off = (int64_t)br.roffset(); bev = EV_ERR; break; }
             bev = EV_MATCH;
             break;
           }

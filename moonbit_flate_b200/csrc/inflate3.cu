@@ -245,7 +245,7 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
                                               const uint8_t *in, int64_t cur_len, uint32_t bend, bool run,
                                               uint32_t start, uint32_t e, uint32_t &p_out, uint32_t &flag_out,
                                               uint32_t &n_out, uint32_t &n_rec, uint8_t *out, uint32_t obase,
-                                              uint2 *rec)
+                                              uint2 *rec, uint32_t h0 = 0)
 {
   const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(sm.lit);
   const uint32_t dist_sa = (uint32_t)__cvta_generic_to_shared(sm.dist);
@@ -324,7 +324,7 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
           if (WRITE) {
             const uint32_t dist = (dt & 0xffffu) + ((dbits >> dl) & ((1u << dxb) - 1u));
             const uint32_t at = obase + cnt_out;
-            if (dist > at) { flag = P_BAD; act = false; } // dist > hist_size (inflate.mbt:677)
+            if (dist > at + h0) { flag = P_BAD; act = false; } // dist > hist_size (inflate.mbt:677), h0 = dictionary
             else rec[cnt_rec] = make_uint2(at, length | ((dist - 1u) << 16));
           }
           cnt_out += length;
@@ -507,6 +507,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
     uint2 *rec = j.records + j.rec_off[st32];
     const uint32_t rec_cap = (uint32_t)(j.rec_off[st32 + 1] - j.rec_off[st32]);
     uint32_t nrec = 0, opos = 0;
+    const uint32_t h0 = j.hist0 ? j.hist0[st32] : 0u; // preset dictionary in front of the slot
     int64_t cur_len = (int64_t)in_len; // bytes from `in` (re-based after every block) to the end
     UBits ub;
     ub.init(in, in_len);
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
                                     opos + xo - (mine ? n_out : 0u));
           else
             decode_ranges<true>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, mine, start, e_i, tp, tf, to, tr, out,
-                                opos + xo - (mine ? n_out : 0u), rec + nrec + xr - (mine ? n_rec : 0u));
+                                opos + xo - (mine ? n_out : 0u), rec + nrec + xr - (mine ? n_rec : 0u), h0);
           const bool bad = mine && (tf == P_BAD || tp != p || to != n_out || tr != n_rec);
           if (__any_sync(kFull, bad)) { bail = true; break; }
         }

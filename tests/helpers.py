@@ -42,6 +42,8 @@ class Oracle:
         L.orc_reader_read.restype = C.c_size_t
         L.orc_reader_read.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
         L.orc_reader_free.argtypes = [C.c_void_p]
+        L.orc_reader_new_dict.restype = C.c_void_p
+        L.orc_reader_new_dict.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         for f in ("orc_token_offset", "orc_reverse16", "orc_reverse_bits", "orc_fixed_chunk"):
             getattr(L, f).restype = C.c_uint32
         L.orc_token_offset.argtypes = [C.c_uint32]
@@ -94,6 +96,21 @@ class Oracle:
         st = self.L.orc_inflate(a.ctypes.data if len(comp) else None, len(comp), out.ctypes.data, cap, C.byref(ol),
                                 C.byref(eo), C.byref(cons))
         return st, out[: ol.value].tobytes(), eo.value, cons.value
+
+    def inflate_dict(self, comp: bytes, dict_: bytes):
+        """&Reader::new_dict(dict) + read until an error / ioeof -> (status, output bytes, err_off)"""
+        a = np.frombuffer(comp, dtype=np.uint8)
+        d = np.frombuffer(dict_, dtype=np.uint8)
+        r = C.c_void_p(self.L.orc_reader_new_dict(a.ctypes.data if len(comp) else None, len(comp),
+                                                  d.ctypes.data if len(dict_) else None, len(dict_)))
+        out = bytearray()
+        buf = np.empty(1 << 16, np.uint8)
+        st, eo = C.c_int(-1), C.c_int64(0)
+        while st.value < 0:
+            k = self.L.orc_reader_read(r, buf.ctypes.data, buf.size, C.byref(st), C.byref(eo))
+            out += buf[:k].tobytes()
+        self.L.orc_reader_free(r)
+        return st.value, bytes(out), eo.value
 
     def huff_generate(self, freq, max_bits):
         f = np.ascontiguousarray(np.asarray(freq, dtype=np.int32))

@@ -426,3 +426,34 @@ def test_multi_block_streams_both_parse_paths(oracle, corpus, monkeypatch, mode)
         assert (st == 0).all() and np.array_equal(out, src)
     finally:
         c.close()
+
+
+def test_reader_preset_dictionary(ctx, oracle, corpus):
+    """&Reader::new_dict / Decompressor::reset (inflate.mbt:310-317, :862-883; DictDecoder::new,
+    dict-decoder.mbt:42-60): streams whose back-references reach into a preset dictionary (made with zlib's
+    zdict: the reference's own Writer::new_dict compresses the dictionary into the output instead, D3).
+    Output, error class and offset equal the oracle's, with the dictionary, without it (the reference then
+    reports corrupt input: dist > hist_size), and for a dictionary longer than the 32 KiB window."""
+    import moonbit_flate_b200 as fb
+
+    for dlen in (100, 5000, 32768, 50000):
+        dict_ = corpus.unit(dlen, seed=91, index=dlen, klass=0)
+        data = dict_[-3000:] + corpus.unit(70000, seed=92, index=dlen, klass=0) + dict_[:2000] + dict_[-500:]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, zdict=dict_)
+        comp = co.compress(data) + co.flush()
+        ost, oout, oeo = oracle.inflate_dict(comp, dict_)
+        assert ost == 0 and oout == data
+        r = fb.Reader.new_dict(comp, dict_, ctx)
+        got, err = r.read_all()
+        assert err is None and got == data, dlen
+        assert r.close() is None
+        # the same stream without its dictionary: the first reference into it is corrupt input, same offset
+        ost2, oout2, oeo2 = oracle.inflate_dict(comp, b"")
+        got2, err2 = fb.Reader.new(comp, ctx).read_all()
+        assert ost2 == fb.ST_CORRUPT and err2 == fb.corrupt_input_error(oeo2) and got2 == oout2, (dlen, err2, oeo2)
+        # reset: same object, other input and dictionary
+        r.reset(comp, dict_)
+        got3, err3 = r.read_all()
+        assert err3 is None and got3 == data
+        r.reset(oracle.deflate(b"plain stream, no dictionary"))
+        assert r.read_all() == (b"plain stream, no dictionary", None)
