@@ -87,6 +87,7 @@ struct fb200_ctx {
   // streams (default), 2 always)
   int blockpar = 1;
   DevBuf bp_flags, bp_idx, bp_tabs, bp_state, bp_list;
+  DevBuf parse_gtables; // hash tables of the parse warps that have no shared-memory table (per GPU)
   DevBuf d_group;                 // [kMaxGroups] u32: K3 work counters
   DevBuf d_group_bounds;          // [kMaxGroups + 1] u64: first block of every group
   uint64_t *h_gbounds = nullptr;  // pinned [kMaxGroups + 1] block bounds, [kMaxGroups + 1] output byte offsets
@@ -225,7 +226,7 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
   }
   ctx->group_done.release();
   ctx->d_group.release();
-  for (DevBuf *b : {&ctx->bp_flags, &ctx->bp_idx, &ctx->bp_tabs, &ctx->bp_state, &ctx->bp_list}) b->release();
+  for (DevBuf *b : {&ctx->bp_flags, &ctx->bp_idx, &ctx->bp_tabs, &ctx->bp_state, &ctx->bp_list, &ctx->parse_gtables}) b->release();
   ctx->d_group_bounds.release();
   for (auto *v : {&ctx->e_gsize, &ctx->e_gdone, &ctx->e_gchain})
     for (cudaEvent_t e : *v) cudaEventDestroy(e);
@@ -465,7 +466,8 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t 
   ctx->stage_end(FB200_STAGE_SETUP);
 
   ctx->stage_begin(FB200_STAGE_PARSE);
-  launch_parse_single(j, ctx->num_sms, st);
+  CK(ctx->parse_gtables.ensure(parse_gtables_bytes(ctx->num_sms)));
+  launch_parse_single(j, ctx->num_sms, ctx->parse_gtables.p, st);
   launches += 1;
   CK(cudaGetLastError());
   {
@@ -474,7 +476,7 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t 
   }
   const bool blockpar = n_multi > 0 && (ctx->blockpar == 2 || (ctx->blockpar == 1 && n_multi < 4096));
   if (n_multi > 0 && !blockpar) {
-    launch_parse_multi(j, ctx->num_sms, st); // one warp per stream, its blocks in sequence
+    launch_parse_multi(j, ctx->num_sms, ctx->parse_gtables.p, st); // one warp per stream, its blocks in sequence
     launches += 1;
   } else if (blockpar) {
     // rounds over the blocks of the multi-block streams (BlockParJob, kernels.h)
@@ -509,7 +511,7 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t 
       launches += 1;
       if (*h_nlist == 0) break;
       bp.nlist = *h_nlist;
-      launch_parse_blocks(j, bp, j.counters + 14, ctx->num_sms, st);
+      launch_parse_blocks(j, bp, j.counters + 14, ctx->num_sms, ctx->parse_gtables.p, st);
       launches += 1;
       rounds++;
       parsed_blocks += bp.nlist;

@@ -579,11 +579,14 @@ void launch_stream_order(const InflateJob &j, uint32_t *order_hist, cudaStream_t
 template <int S>
 static void launch_decode(const InflateJob &j, int num_sms, cudaStream_t st)
 {
-  static bool inited = false;
+  static bool inited[64] = {}; // function attributes are per device
   const int smem = (kDecStreamsPerCta / S) * (int)sizeof(DecSmem<S>);
-  if (!inited) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev >= 0 && dev < 64 ? dev : 0;
+  if (!inited[dev]) {
     cudaFuncSetAttribute(k_inflate_decode<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    inited = true;
+    inited[dev] = true;
   }
   const uint64_t want = (j.nstreams + kDecStreamsPerCta - 1) / kDecStreamsPerCta;
   const uint64_t maxg = (uint64_t)num_sms * 4; // 4 CTAs (128 streams) per SM by shared memory

@@ -68,15 +68,19 @@ void launch_count_blocks(const DeflateJob &j, cudaStream_t st);
 void launch_count_multi(const DeflateJob &j, cudaStream_t st);
 void launch_fill_blocks(const DeflateJob &j, cudaStream_t st);
 // K1: greedy LZ77 parse, one warp per stream (deflate-fast.mbt:123-342)
-void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st);
+// gtables: parse_gtables_bytes(num_sms) bytes of device scratch on the launching GPU (tables of the warps that have
+// no shared-memory table)
+size_t parse_gtables_bytes(int num_sms);
+void launch_parse(const DeflateJob &j, int num_sms, void *gtables, cudaStream_t st);
 // the two halves of launch_parse: streams with one parsed block / streams with several (sequential per stream)
-void launch_parse_single(const DeflateJob &j, int num_sms, cudaStream_t st);
-void launch_parse_multi(const DeflateJob &j, int num_sms, cudaStream_t st);
+void launch_parse_single(const DeflateJob &j, int num_sms, void *gtables, cudaStream_t st);
+void launch_parse_multi(const DeflateJob &j, int num_sms, void *gtables, cudaStream_t st);
 // block-parallel rounds for the multi-block streams (see BlockParJob)
 void launch_bp_flags(const DeflateJob &j, uint64_t *flags, cudaStream_t st);
 void launch_bp_round(const DeflateJob &j, const BlockParJob &bp, const uint8_t *chg_prev, uint32_t *list, uint32_t *nlist,
                      cudaStream_t st);
-void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *counter, int num_sms, cudaStream_t st);
+void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *counter, int num_sms, void *gtables,
+                         cudaStream_t st);
 // FB200_PARSE_L2PERSIST=1 only: to be called once the parse has completed (un-pins its L2 lines); returns at once otherwise
 void parse_release_l2();
 bool parse_uses_l2_persistence();

@@ -654,8 +654,15 @@ void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
 // (21.6 vs 20.0 ms per GiB at 5 + 18 warps): sharing the two memory trips does not pay for the extra work per
 // batch.  Compiled out by default.
 static int g_parse_occ_single = 0, g_parse_occ_multi = 0, g_parse_gwarps = 0, g_parse_wide = 0;
-static void *g_parse_gtables = nullptr;
 static int g_parse_persist = -1;
+constexpr int kMaxDevices = 64;
+
+static int current_device()
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
 
 // After the parse has finished: lines the persistence window pinned in L2 go back to normal, so that the
 // set-aside part of L2 serves the kernels that follow (left pinned, it cost the inflate 2.4 ms per GiB).
@@ -668,8 +675,9 @@ void parse_release_l2()
 
 static void parse_init(int num_sms)
 {
-  static bool inited = false;
-  if (!inited) {
+  (void)num_sms;
+  static bool configured = false;
+  if (!configured) { // warp mix: once per process
     const char *e = getenv("FB200_PARSE_WARPS");
     int w = e ? atoi(e) : 5;
     if (w < 0) w = 0;
@@ -684,30 +692,37 @@ static void parse_init(int num_sms)
     g_parse_occ_single = w;
     g_parse_occ_multi = w > 3 ? 3 : w;
     g_parse_gwarps = gw;
-    if (gw) cudaMalloc(&g_parse_gtables, (size_t)num_sms * gw * kTableSize * 4);
+    configured = true;
+  }
+  static bool attr_set[kMaxDevices] = {}; // function attributes are per device
+  const int dev = current_device();
+  if (!attr_set[dev]) {
+    const int gw = g_parse_gwarps;
     cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_parse_occ_single * kTableSize * 2 + gw * (g_parse_wide ? kWideScratch : 0));
     cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0));
     cudaFuncSetAttribute(k_parse_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, g_parse_occ_multi * kTableSize * 4);
-    inited = true;
-  }
-  {
+    const char *co = getenv("FB200_PARSE_CARVEOUT");
+    const int pct = co ? atoi(co) : -1;
     // Shared-memory carve-out: by default the smallest one that holds the tables (5 tables -> 164 KB, 92 KB of
     // L1).  Measured with 5 + 25 warps: 196 KB carve-out 19.8 ms per GiB, 228 KB 30.7 ms, default 18.6 ms.
-    static int pct_set = -2;
-    if (pct_set == -2) {
-      const char *co = getenv("FB200_PARSE_CARVEOUT");
-      pct_set = co ? atoi(co) : -1;
-      if (pct_set >= 0) {
-        cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct_set);
-        cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct_set);
-      }
+    if (pct >= 0) {
+      cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
+    attr_set[dev] = true;
   }
 }
 
-void launch_parse_single(const DeflateJob &j, int num_sms, cudaStream_t st)
+// bytes of global-table scratch launch_parse_* needs (owned by the context: one per GPU)
+size_t parse_gtables_bytes(int num_sms)
+{
+  parse_init(num_sms);
+  return (size_t)num_sms * (size_t)(g_parse_gwarps ? g_parse_gwarps : 1) * kTableSize * 4;
+}
+
+void launch_parse_single(const DeflateJob &j, int num_sms, void *gtables, cudaStream_t st)
 {
   parse_init(num_sms);
   const int gw = g_parse_gwarps;
@@ -733,7 +748,7 @@ void launch_parse_single(const DeflateJob &j, int num_sms, cudaStream_t st)
     size_t bytes = (size_t)num_sms * gw * kTableSize * 2;
     if ((size_t)maxw < bytes) bytes = (size_t)maxw;
     cudaStreamAttrValue av{};
-    av.accessPolicyWindow.base_ptr = g_parse_gtables;
+    av.accessPolicyWindow.base_ptr = gtables;
     av.accessPolicyWindow.num_bytes = bytes;
     av.accessPolicyWindow.hitRatio = bytes <= (size_t)maxp ? 1.0f : (float)((double)maxp / (double)bytes);
     av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -741,7 +756,7 @@ void launch_parse_single(const DeflateJob &j, int num_sms, cudaStream_t st)
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
   }
   k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * 2 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
-      j, j.counters + 0, g_parse_occ_single, g_parse_gtables, g_parse_wide);
+      j, j.counters + 0, g_parse_occ_single, gtables, g_parse_wide);
   if (persist && gw) {
     cudaStreamAttrValue av{};
     av.accessPolicyWindow.num_bytes = 0;
@@ -749,18 +764,18 @@ void launch_parse_single(const DeflateJob &j, int num_sms, cudaStream_t st)
   }
 }
 
-void launch_parse_multi(const DeflateJob &j, int num_sms, cudaStream_t st)
+void launch_parse_multi(const DeflateJob &j, int num_sms, void *gtables, cudaStream_t st)
 {
   parse_init(num_sms);
   const int gw = g_parse_gwarps;
   k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
-      j, j.counters + 1, g_parse_occ_multi, g_parse_gtables, g_parse_wide);
+      j, j.counters + 1, g_parse_occ_multi, gtables, g_parse_wide);
 }
 
-void launch_parse(const DeflateJob &j, int num_sms, cudaStream_t st)
+void launch_parse(const DeflateJob &j, int num_sms, void *gtables, cudaStream_t st)
 {
-  launch_parse_single(j, num_sms, st);
-  launch_parse_multi(j, num_sms, st);
+  launch_parse_single(j, num_sms, gtables, st);
+  launch_parse_multi(j, num_sms, gtables, st);
 }
 
 void launch_bp_flags(const DeflateJob &j, uint64_t *flags, cudaStream_t st)
@@ -776,12 +791,13 @@ void launch_bp_round(const DeflateJob &j, const BlockParJob &bp, const uint8_t *
   k_bp_round<<<(unsigned)((j.nblocks + 255) / 256), 256, 0, st>>>(j, bp, chg_prev, list, nlist);
 }
 
-void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *counter, int num_sms, cudaStream_t st)
+void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *counter, int num_sms, void *gtables,
+                         cudaStream_t st)
 {
   parse_init(num_sms);
   const int gw = g_parse_gwarps;
   k_parse_blocks<<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4, st>>>(
-      j, bp, counter, g_parse_occ_multi, g_parse_gtables);
+      j, bp, counter, g_parse_occ_multi, gtables);
 }
 
 // ------------------------------------------------------------------

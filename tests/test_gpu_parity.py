@@ -457,3 +457,28 @@ def test_reader_preset_dictionary(ctx, oracle, corpus):
         assert err3 is None and got3 == data
         r.reset(oracle.deflate(b"plain stream, no dictionary"))
         assert r.read_all() == (b"plain stream, no dictionary", None)
+
+
+def test_two_contexts_two_gpus_one_process(oracle, corpus):
+    """One context per GPU inside ONE process (the C ABI's contract): device scratch and kernel attributes are
+    per context / per device.  Skipped on a single-GPU box."""
+    import torch
+    import moonbit_flate_b200 as fb
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctxs = [fb.Context(0), fb.Context(1)]
+    try:
+        src = corpus.fill(96, 65536, seed=13)
+        long_stream = corpus.fill(12, 65536, seed=14)  # one multi-block stream: block-parallel parse
+        for rep in range(2):
+            for c in ctxs:
+                comp, off = c.deflate_segments(src, 65536)
+                for i in range(0, 96, 17):
+                    assert comp[int(off[i]): int(off[i + 1])].tobytes() == oracle.deflate(src[i * 65536:(i + 1) * 65536].tobytes())
+                out, olen, st, eo, cons = c.inflate_batch(comp, off, np.arange(97, dtype=np.uint64) * 65536)
+                assert (st == 0).all() and np.array_equal(out, src)
+                assert c.deflate(long_stream.tobytes()) == oracle.deflate(long_stream.tobytes())
+    finally:
+        for c in ctxs:
+            c.close()
