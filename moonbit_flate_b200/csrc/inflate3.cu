@@ -42,7 +42,13 @@ constexpr uint32_t kLitLim = 256u << 4; // table entry = (symbol << 4) | code le
 constexpr uint32_t P_OK = 0, P_EOB = 1, P_BAD = 2;
 constexpr uint32_t kMinRange = 256;     // bits per lane at least
 constexpr int kLaneCopyMax = 16;
-constexpr uint32_t kPrefetchWords = 24;  // lane read-ahead: three 32-byte sectors
+#ifndef FB_INF_PF
+#define FB_INF_PF 1 // lane read-ahead: 0 none, 1 into L1, 2 into L2 only
+#endif
+#ifndef FB_INF_PF_WORDS
+#define FB_INF_PF_WORDS 24
+#endif
+constexpr uint32_t kPrefetchWords = FB_INF_PF_WORDS;  // lane read-ahead: three 32-byte sectors
 constexpr uint32_t kSyncBits = 1536;   // round-0 run-in of a lane (bits)
 
 struct Tab {
@@ -210,7 +216,11 @@ struct LBits {
       bo -= 32;
       // every lane streams through its own range: without this each 32-byte sector is a demand miss, and
       // with 32 lanes in different places a warp would be waiting on one of them at nearly every step
+#if FB_INF_PF == 2
+      if ((wi & 7u) == 0u && wi + kPrefetchWords < nwords) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + wi + kPrefetchWords));
+#elif FB_INF_PF == 1
       if ((wi & 7u) == 0u && wi + kPrefetchWords < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + kPrefetchWords));
+#endif
     }
   }
   __device__ __forceinline__ uint32_t abit() const { return (wi << 5) + (uint32_t)bo; }
