@@ -255,3 +255,30 @@ def test_reader_hands_out_window_flushes(oracle, corpus):
     oracle.L.orc_reader_free(r)
     assert got == d and st.value == ORC_OK
     assert chunks[:3] == [32768, 32768, 32768] and max(chunks) == 32768
+
+
+def test_deflate_bound_covers_worst_cases():
+    """fb200_deflate_stream_bound / fb200_deflate_bound (the capacity a caller allocates) against what the
+    reference's encoder really emits for its worst inputs: incompressible bytes (literal-only Huffman blocks,
+    ~1.001 x, never stored: D2), tiny streams (5..26 bytes of framing), skewed alphabets (15-bit codes)."""
+    import ctypes as C
+    import moonbit_flate_b200 as fb
+    L = fb._lib
+    o = Oracle()
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for n in [0, 1, 2, 15, 16, 17, 100, 127, 128, 129, 1000, 65534, 65535, 65536, 65537, 65662, 65663, 131070, 200001]:
+        for kind in range(3):
+            if kind == 0:
+                d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            elif kind == 1:
+                p = 0.93 ** np.arange(256); p /= p.sum()
+                d = rng.choice(256, size=n, p=p).astype(np.uint8).tobytes()
+            else:
+                d = bytes(n)
+            c = len(o.deflate(d))
+            b = L.fb200_deflate_stream_bound(n)
+            assert c <= b, (n, kind, c, b)
+            worst = max(worst, c / max(b, 1))
+            assert c <= L.fb200_deflate_bound(n, 65536) or n == 0, (n, kind)
+    assert worst < 0.75  # the bound is generous, not tight
