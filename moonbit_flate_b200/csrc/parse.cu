@@ -64,6 +64,11 @@ constexpr bool kGtabPrefetch = FB_GTAB_PREFETCH != 0;
 #ifndef FB_PF
 #define FB_PF 1
 #endif
+// Tagged table entries for single-block streams (experiment): position (16 bits) + 16 more bits of the hash
+// product, so that a candidate whose 4 bytes cannot be equal is rejected without reading the source.
+#ifndef FB_TAGS
+#define FB_TAGS 0
+#endif
 #ifndef FB_WIDE_BATCH
 #define FB_WIDE_BATCH 0 // compiled out by default: it costs 16 registers (= 4 warps per SM) and measured slower
 #endif
@@ -101,6 +106,8 @@ __device__ __forceinline__ int match_tail(const uint8_t *srcb, int s2, int t, in
   }
   return a;
 }
+
+__device__ __forceinline__ uint32_t tag_of(uint32_t cv) { return ((cv * kHashMul) >> 2) & 0xffffu; }
 
 template <bool MULTI, typename T, bool GTAB>
 __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table, uint8_t *scratch, int wide,
@@ -330,7 +337,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           const uint32_t h = hash4(cv);
           T *slot = table + h;
           const T old = *slot; // (ld.global.cg for the global tables: measured, no difference)
-          const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
+          const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)((FB_TAGS ? (tag_of(cv) << 16) : 0u) | (uint32_t)pos);
           T la_old = 0;
           bool la_ok = false;
           if (FB_PF && !MULTI && pos + 36 <= n) {
@@ -360,8 +367,9 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
             ok = (old != 0) && (D <= (uint32_t)kMaxMatchOffset);
             cand = pos - (int)D;
           } else {
-            cand = (int)old;
+            cand = (int)((uint32_t)old & 0xffffu);
             ok = (uint32_t)(pos - cand - 1) < (uint32_t)kMaxMatchOffset;
+            if (FB_TAGS) ok = ok && (((uint32_t)old >> 16) == tag_of(cv)); // different tag: the 4 bytes differ
           }
           ok = ok && (lane != 0);
           // 12 bytes at the candidate (own position when there is none: harmless L1 hit)
@@ -500,9 +508,10 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           ok = (old != 0) && (D <= (uint32_t)kMaxMatchOffset);
           cand = pos - (int)D;
         } else {
-          const int D = pos - (int)old;
+          cand = (int)((uint32_t)old & 0xffffu);
+          const int D = pos - cand;
           ok = (D >= 1) && (D <= kMaxMatchOffset);
-          cand = (int)old;
+          if (FB_TAGS) ok = ok && (((uint32_t)old >> 16) == tag_of(cv));
         }
         bool hit = false;
         if (active && probe && ok) hit = (ld32u(srcb + cand) == cv); // :196
@@ -514,7 +523,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         const bool committed = active && ((cmask >> lane) & 1u);
         const unsigned cm = __ballot_sync(kFull, committed);
         if (committed && (peers & cm & gt_mask) == 0) // last writer of this bucket in program order
-          table[h] = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
+          table[h] = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)((FB_TAGS ? (tag_of(cv) << 16) : 0u) | (uint32_t)pos);
         __syncwarp();
 
         if (m == 32) { // 32 misses: keep probing (:198-199)
@@ -583,7 +592,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
 template <bool MULTI>
 __global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *gtables, int wide)
 {
-  using T = typename std::conditional<MULTI, uint32_t, uint16_t>::type;
+  using T = typename std::conditional<MULTI || FB_TAGS, uint32_t, uint16_t>::type;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   if (warp < smem_warps) {
@@ -689,6 +698,7 @@ static void parse_init(int num_sms)
     if (w + gw == 0) w = 1;
     if (w + gw > 32) gw = 32 - w; // one CTA per SM, at most 1024 threads
     if (const char *wd = getenv("FB200_PARSE_WIDE")) g_parse_wide = kWideBatch && atoi(wd) != 0;
+    if (FB_TAGS && w > 3) w = 3; // 64 KB per table
     g_parse_occ_single = w;
     g_parse_occ_multi = w > 3 ? 3 : w;
     g_parse_gwarps = gw;
@@ -699,7 +709,7 @@ static void parse_init(int num_sms)
   if (!attr_set[dev]) {
     const int gw = g_parse_gwarps;
     cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         g_parse_occ_single * kTableSize * 2 + gw * (g_parse_wide ? kWideScratch : 0));
+                         g_parse_occ_single * kTableSize * (FB_TAGS ? 4 : 2) + gw * (g_parse_wide ? kWideScratch : 0));
     cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0));
     cudaFuncSetAttribute(k_parse_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, g_parse_occ_multi * kTableSize * 4);
@@ -755,7 +765,7 @@ void launch_parse_single(const DeflateJob &j, int num_sms, void *gtables, cudaSt
     av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
   }
-  k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * 2 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
+  k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * (FB_TAGS ? 4 : 2) + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
       j, j.counters + 0, g_parse_occ_single, gtables, g_parse_wide);
   if (persist && gw) {
     cudaStreamAttrValue av{};
