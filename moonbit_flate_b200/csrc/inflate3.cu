@@ -422,13 +422,16 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
 // Replays records [0, nrec) of one stream in order.
 __device__ void replay_records(uint8_t *out, const uint2 *rec, uint32_t nrec, int lane)
 {
+  uint2 nxt = make_uint2(0u, 0u); // the next group's records are requested while this group is being copied
+  if ((uint32_t)lane < nrec) nxt = rec[lane];
   for (uint32_t g = 0; g < nrec; g += 32) {
     const uint32_t r = g + (uint32_t)lane;
     uint32_t dst = 0, len = 0, dist = 1;
     if (r < nrec) {
-      const uint2 v = rec[r];
+      const uint2 v = nxt;
       dst = v.x; len = v.y & 0xffffu; dist = (v.y >> 16) + 1u;
     }
+    if (r + 32u < nrec) nxt = rec[r + 32u];
     const bool big = len > (uint32_t)kLaneCopyMax;
     // source interval: [dst - dist, dst - dist + min(len, dist))
     const uint32_t src_end = dst - dist + (len < dist ? len : dist);
