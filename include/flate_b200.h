@@ -214,6 +214,24 @@ int fb200_last_stage_ms(const fb200_ctx *ctx, float *ms);
 int fb200_last_blocks(const fb200_ctx *ctx, uint32_t *blk_ntok, uint8_t *blk_kind, uint32_t *blk_bits,
                       uint64_t blk_cap, uint32_t *tokens, uint64_t tok_cap);
 
+/* Test hook: 1 if block b of one stream starts with a cleared hash table (DeflateFast::encode calls
+ * shift_offsets once cur has reached buffer_reset, deflate-fast.mbt:129-132); the closed form the
+ * block-parallel parse uses, checked against the running sum by tests/test_abi.py. */
+int fb200_debug_block_resets(uint64_t b);
+
+/* ------------------------------------------------------------------ */
+/* Environment switches read at fb200_create (everything else is compiled in):
+ *   FB200_HOST_OVERLAP=0|1    host-buffer calls: overlap the H2D copy with the consuming kernel through a device
+ *                             watermark (default 1; default 0 when CUDA_LAUNCH_BLOCKING is set or a profiler /
+ *                             sanitizer / debugger injection variable is present: copy first, then launch)
+ *   FB200_CHUNK_MB=n          size of the H2D chunks / D2H output groups of the host-buffer calls (32)
+ *   FB200_GROUP_MB=n          input per K2..K4 group of the host-buffer deflate (64)
+ *   FB200_DEFLATE_PIPELINE=0  host-buffer deflate: K2..K4 in one piece instead of group by group
+ *   FB200_PARSE_BLOCKPAR=0|1|2  block-parallel parse of multi-block streams: never / when few streams / always
+ *   FB200_PARSE_WARPS=s, FB200_PARSE_GWARPS=g  parse warps per SM with shared-memory / global-memory tables
+ *   FB200_INFLATE_CTAS=c      inflate CTAs (4 warps each) per SM
+ *   FB200_TRACE=1             timeline of the host-buffer calls on stderr */
+
 #ifdef __cplusplus
 }
 #endif

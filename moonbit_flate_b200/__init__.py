@@ -98,6 +98,7 @@ ABI = {
     "fb200_last_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "fb200_cuda_stream": (C.c_void_p, [C.c_void_p]),
     "fb200_last_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fb200_debug_block_resets": (C.c_int, [C.c_uint64]),
     "fb200_last_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
 }
 for _name, (_res, _args) in ABI.items():

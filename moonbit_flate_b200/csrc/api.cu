@@ -65,9 +65,6 @@ struct fb200_ctx {
   DevBuf p_in[2], p_out[2], p_off_in[2], p_off_out[2], p_off_abs[2], p_len[2], p_status[2], p_eoff[2], p_cons[2];
   DevBuf all_off, all_off2;
   DevBuf i_fallback, i_rec_off, i_nrec, i_records, i_order, i_order_hist;
-  // fast path of the inflate: 3 = warp per stream, lanes decode a block in parallel (inflate3.cu, default);
-  // 1 = warp per stream, warp-uniform decode (inflate.cu); 2 = thread per stream (inflate2.cu, experimental)
-  int inflate_mode = 3;
   uint32_t *d_wm = nullptr;        // [2] arrival watermarks (deflate, inflate) advanced by the H2D stream
   uint32_t *wm_vals = nullptr;     // pinned: the values the H2D stream copies into d_wm, one per chunk
   volatile uint32_t *h_flags = nullptr; // mapped pinned: inflate output groups finished on the device
@@ -95,6 +92,12 @@ struct fb200_ctx {
   cudaEvent_t e_bounds = nullptr, e_parsed = nullptr;
   cudaEvent_t e_in[2] = {}, e_comp[2] = {}, e_out[2] = {};
   uint64_t chunk_bytes = 32ull << 20;
+  // Host-buffer calls overlap the H2D copy with the kernel that consumes it: the kernel waits on a device watermark
+  // the copy stream advances.  All copies are queued BEFORE the kernel is launched, so a launch that blocks the
+  // host (CUDA_LAUNCH_BLOCKING, a debugger) cannot deadlock; tools that replay kernels (ncu restores device memory,
+  // the watermark included, between passes) need the copies to have finished before the launch, which is what
+  // overlap_h2d == false selects: no watermark, the kernel is ordered behind the last chunk.
+  bool overlap_h2d = true;
   uint64_t *pinned = nullptr; // small pinned read-back area
   // last deflate job (for introspection)
   DeflateJob last{};
@@ -120,6 +123,22 @@ struct fb200_ctx {
   } while (0)
 
 extern "C" int fb200_version(void) { return FB200_VERSION; }
+
+extern char **environ;
+
+// A tool that serialises kernel launches or replays kernels is attached to this process (Nsight Compute,
+// compute-sanitizer, cuda-gdb inject through these variables), or launches were made blocking.
+static bool serialising_tool_attached()
+{
+  if (const char *e = getenv("CUDA_LAUNCH_BLOCKING"))
+    if (*e && strcmp(e, "0") != 0) return true;
+  static const char *const prefixes[] = {"CUDA_INJECTION", "NV_COMPUTE_PROFILER_", "NV_NSIGHT_", "NV_TPS_LAUNCH",
+                                         "NVTX_INJECTION", "NV_SANITIZER_", "COMPUTE_SANITIZER_", "CUDA_DEBUGGER_"};
+  for (char **e = environ; e && *e; e++)
+    for (const char *p : prefixes)
+      if (strncmp(*e, p, strlen(p)) == 0) return true;
+  return false;
+}
 
 // test hook (not part of the public header): the closed form the block-parallel parse uses for "this block starts
 // with a cleared table" (deflate-fast.mbt:129-132)
@@ -170,6 +189,9 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   cudaStreamCreateWithFlags(&ctx->s_post2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->e_bounds, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->e_parsed, cudaEventDisableTiming);
+  // FB200_HOST_OVERLAP: 1 forces the watermark overlap on, 0 off; unset = on unless a serialising tool is attached
+  ctx->overlap_h2d = !serialising_tool_attached();
+  if (const char *e = getenv("FB200_HOST_OVERLAP")) ctx->overlap_h2d = atoi(e) != 0;
   if (const char *e = getenv("FB200_DEFLATE_PIPELINE")) ctx->pipeline = atoi(e) != 0;
   if (const char *e = getenv("FB200_PARSE_BLOCKPAR")) ctx->blockpar = atoi(e);
   if (const char *e = getenv("FB200_GROUP_MB")) {
@@ -185,10 +207,6 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   cudaMallocHost((void **)&ctx->wm_vals, fb200_ctx::kMaxChunks * sizeof(uint32_t));
   cudaHostAlloc((void **)&ctx->h_flags, fb200_ctx::kMaxChunks * sizeof(uint32_t), cudaHostAllocMapped);
   if (!ctx->d_wm || !ctx->wm_vals || !ctx->h_flags) { cudaGetLastError(); fb200_destroy(ctx); return FB200_ERR_CUDA; }
-  if (const char *e = getenv("FB200_INFLATE_MODE")) {
-    const int m = atoi(e);
-    if (m >= 1 && m <= 3) ctx->inflate_mode = m;
-  }
   if (const char *e = getenv("FB200_CHUNK_MB")) {
     const long mb = atol(e);
     if (mb > 0) ctx->chunk_bytes = (uint64_t)mb << 20;
@@ -196,7 +214,6 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   preload_parse_kernels();
   preload_encode_kernels();
   preload_inflate_kernels();
-  preload_inflate2_kernels();
   preload_inflate3_kernels();
   launch_init_tables(ctx->stream);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -360,8 +377,7 @@ struct DeflateIo {
   uint64_t h_cap = 0;
 };
 
-template <typename Feed>
-static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t *total_out)
+static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
 {
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -470,10 +486,6 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, Feed feed, uint64_t 
   launch_parse_single(j, ctx->num_sms, ctx->parse_gtables.p, st);
   launches += 1;
   CK(cudaGetLastError());
-  {
-    const int rc = feed(); // host-buffer calls: queue the H2D chunks + watermark updates
-    if (rc != FB200_OK) return rc;
-  }
   const bool blockpar = n_multi > 0 && (ctx->blockpar == 2 || (ctx->blockpar == 1 && n_multi < 4096));
   if (n_multi > 0 && !blockpar) {
     launch_parse_multi(j, ctx->num_sms, ctx->parse_gtables.p, st); // one warp per stream, its blocks in sequence
@@ -642,7 +654,7 @@ extern "C" int fb200_deflate_streams_dev(fb200_ctx *ctx, const uint8_t *d_src, c
   io.d_dst = d_dst;
   io.d_cap = dst_cap;
   uint64_t total = 0;
-  const int rc = deflate_run(ctx, io, [] { return FB200_OK; }, &total);
+  const int rc = deflate_run(ctx, io, &total);
   *out_len = total;
   return rc;
 }
@@ -665,6 +677,7 @@ extern "C" int fb200_deflate_segments_dev(fb200_ctx *ctx, const uint8_t *d_src, 
 // on a second stream, and after every chunk that stream advances a device watermark ("streams whose bytes
 // have arrived") which the parse waits on, so the H2D copy runs beside the parse instead of in front of it.
 // Chunk boundaries are rounded up to 128 bytes: a cache line never holds bytes of two different arrivals.
+// Every copy and watermark update is queued before the parse is launched (see fb200_ctx::overlap_h2d).
 static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, const uint64_t *src_off, uint64_t ns,
                                uint64_t seg_size, uint8_t *dst, uint64_t dst_cap, uint64_t *dst_off, uint64_t *out_len)
 {
@@ -740,13 +753,13 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
   io.nb_known = nb;
   io.n_multi = n_multi;
   io.nmb = nmb;
-  io.avail = ctx->d_wm;
+  io.avail = ctx->overlap_h2d ? ctx->d_wm : nullptr;
   io.d_dst = ctx->p_out[0].as<uint8_t>();
   io.d_cap = dcap;
   io.h_dst = dst;
   io.h_cap = dst_cap;
-  // once the kernels are queued: feed them
-  auto feed = [&]() -> int {
+  // the feed: input chunks + watermark updates on the copy stream, all queued before any kernel that waits on them
+  {
     uint64_t done = 0;
     for (size_t c = 0; c < cuts.size(); c++) {
       uint64_t upto = c + 1 == cuts.size() ? n : ((cuts[c].bytes + 127) & ~127ull);
@@ -755,13 +768,18 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
         CK(cudaMemcpyAsync(d_src + done, src + base0 + done, upto - done, cudaMemcpyHostToDevice, ctx->s_in));
         done = upto;
       }
-      ctx->wm_vals[c] = (uint32_t)cuts[c].streams;
-      CK(cudaMemcpyAsync(ctx->d_wm, &ctx->wm_vals[c], 4, cudaMemcpyHostToDevice, ctx->s_in));
+      if (ctx->overlap_h2d) {
+        ctx->wm_vals[c] = (uint32_t)cuts[c].streams;
+        CK(cudaMemcpyAsync(ctx->d_wm, &ctx->wm_vals[c], 4, cudaMemcpyHostToDevice, ctx->s_in));
+      }
     }
-    return FB200_OK;
-  };
+    if (!ctx->overlap_h2d) { // copy, then launch
+      CK(cudaEventRecord(ctx->e_in[1], ctx->s_in));
+      CK(cudaStreamWaitEvent(st, ctx->e_in[1], 0));
+    }
+  }
   uint64_t total = 0;
-  const int rc = deflate_run(ctx, io, feed, &total);
+  const int rc = deflate_run(ctx, io, &total);
   *out_len = total;
   if (rc != FB200_OK) {
     cudaStreamSynchronize(ctx->s_in);
@@ -890,9 +908,7 @@ static int inflate_launch(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t 
   j.group_streams = hk.group_streams;
   for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
   uint64_t launches = nstreams ? 2 : 0;
-  int mode = ctx->inflate_mode;
-  if (mode == 2 && (hk.avail || hk.hist0)) mode = 3; // the overlapped host path and dictionaries are wired into modes 1 and 3
-  if (mode != 1 && nstreams) {
+  if (nstreams) {
     // record areas: sized from the output capacity (a match yields >= 3 bytes)
     uint64_t cap_total = cap_total_known;
     if (cap_total == ~0ull) {
@@ -911,17 +927,14 @@ static int inflate_launch(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t 
     CK(ctx->i_order_hist.ensure(1024 * 4));
     j.order = ctx->i_order.as<uint32_t>();
     launch_rec_off(d_out_off, ctx->i_rec_off.as<uint64_t>(), nstreams, st);
-    launches += mode == 2 ? 5 : 1;
-    if (mode == 3) {
-      // longest streams first -- unless a host-buffer call wants output groups to finish in index order
-      if (hk.avail) j.order = nullptr;
-      else { launch_stream_order(j, ctx->i_order_hist.as<uint32_t>(), st); launches += 3; }
-    }
+    launches += 1;
+    // longest streams first -- unless a host-buffer call wants output groups to finish in index order
+    if (hk.group_done) j.order = nullptr;
+    else { launch_stream_order(j, ctx->i_order_hist.as<uint32_t>(), st); launches += 3; }
   }
   ctx->stage_begin(FB200_STAGE_INFLATE);
-  if (mode == 2) launch_inflate2(j, ctx->num_sms, ctx->i_order_hist.as<uint32_t>(), st);
-  else if (mode == 3) launch_inflate3(j, ctx->num_sms, st);
-  launch_inflate(j, ctx->num_sms, mode == 1, st);
+  launch_inflate3(j, ctx->num_sms, st);
+  launch_inflate_exact(j, ctx->num_sms, st);
   ctx->stage_end(FB200_STAGE_INFLATE);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->pinned, j.counters, 32, cudaMemcpyDeviceToHost, st));
@@ -972,7 +985,6 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
   if (nstreams == 0) return FB200_OK;
   if (nstreams > 0xfffffff0ull) return FB200_ERR_ARG;
   cudaStream_t st = ctx->stream;
-  const bool overlap = ctx->inflate_mode != 2;
   // output groups: ~chunk_bytes of output capacity each, at most kMaxChunks of them
   uint64_t gs = no ? (uint64_t)((double)ctx->chunk_bytes / ((double)no / (double)nstreams)) : nstreams;
   if (gs == 0) gs = 1;
@@ -1006,22 +1018,9 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
   double t_first = 0, t_last = 0, t_fed = 0;
-  InflateHooks hk;
-  if (overlap) {
-    hk.avail = ctx->d_wm + 1;
-    hk.group_done = ctx->group_done.as<uint32_t>();
-    hk.group_flag = ctx->h_flags;
-    hk.group_streams = (uint32_t)gs;
-  } else {
-    // everything resident before the kernels start
-    if (nc) CK(cudaMemcpyAsync(d_comp, comp + c0, nc, cudaMemcpyHostToDevice, st));
-  }
-  int rc = inflate_launch(ctx, d_comp, ctx->p_off_in[0].as<uint64_t>(), nstreams, d_out, ctx->p_off_out[0].as<uint64_t>(),
-                          ctx->p_len[0].as<uint64_t>(), ctx->p_status[0].as<int32_t>(), ctx->p_eoff[0].as<int64_t>(),
-                          ctx->p_cons[0].as<uint64_t>(), no, hk);
-  if (rc != FB200_OK) return rc;
-  if (overlap) {
-    // feed the kernel: input chunks (boundaries rounded up to 128 bytes) + watermark
+  // the feed first: input chunks (boundaries rounded up to 128 bytes) + watermark updates on the copy stream,
+  // all queued before the kernel that waits on them is launched (see fb200_ctx::overlap_h2d)
+  {
     uint64_t step = ctx->chunk_bytes;
     if (nc / step + 2 > (uint64_t)fb200_ctx::kMaxChunks) step = nc / (fb200_ctx::kMaxChunks - 2) + 1;
     uint64_t done = 0, next_cut = step;
@@ -1035,13 +1034,30 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
           CK(cudaMemcpyAsync(d_comp + done, comp + c0 + done, upto - done, cudaMemcpyHostToDevice, ctx->s_in));
           done = upto;
         }
-        ctx->wm_vals[c] = (uint32_t)(i + 1);
-        CK(cudaMemcpyAsync(ctx->d_wm + 1, &ctx->wm_vals[c], 4, cudaMemcpyHostToDevice, ctx->s_in));
+        if (ctx->overlap_h2d) {
+          ctx->wm_vals[c] = (uint32_t)(i + 1);
+          CK(cudaMemcpyAsync(ctx->d_wm + 1, &ctx->wm_vals[c], 4, cudaMemcpyHostToDevice, ctx->s_in));
+        }
         c++;
         next_cut = endb + step;
       }
     }
-    t_fed = now();
+    if (!ctx->overlap_h2d) { // copy, then launch
+      CK(cudaEventRecord(ctx->e_in[1], ctx->s_in));
+      CK(cudaStreamWaitEvent(st, ctx->e_in[1], 0));
+    }
+  }
+  t_fed = now();
+  InflateHooks hk;
+  hk.avail = ctx->overlap_h2d ? ctx->d_wm + 1 : nullptr;
+  hk.group_done = ctx->group_done.as<uint32_t>();
+  hk.group_flag = ctx->h_flags;
+  hk.group_streams = (uint32_t)gs;
+  int rc = inflate_launch(ctx, d_comp, ctx->p_off_in[0].as<uint64_t>(), nstreams, d_out, ctx->p_off_out[0].as<uint64_t>(),
+                          ctx->p_len[0].as<uint64_t>(), ctx->p_status[0].as<int32_t>(), ctx->p_eoff[0].as<int64_t>(),
+                          ctx->p_cons[0].as<uint64_t>(), no, hk);
+  if (rc != FB200_OK) return rc;
+  {
     // drain: copy every output group back as soon as the device reports it finished
     for (uint64_t g = 0; g < ngroups; g++) {
       unsigned spins = 0;
@@ -1059,7 +1075,7 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
   rc = inflate_finish(ctx);
   if (rc != FB200_OK) return rc;
   const double t_kdone = now();
-  if (!overlap || ctx->stats.inflate_fallbacks) { // (re-)copy the whole output: exact-kernel results came last
+  if (ctx->stats.inflate_fallbacks) { // re-copy the whole output: exact-kernel results came last
     CK(cudaStreamSynchronize(ctx->s_out));
     if (no) CK(cudaMemcpyAsync(out + o0, d_out, no, cudaMemcpyDeviceToHost, st));
   } else {
@@ -1310,8 +1326,11 @@ extern "C" uint64_t fb200_reader_read(fb200_reader *r, uint8_t *buf, uint64_t n,
     if (err_off) *err_off = r->err_off;
     return 0;
   }
+  // DictDecoder::new starts with wr_pos = the dictionary length (mod the window, dict-decoder.mbt:56-62), so the
+  // window flushes fall where (D + position) is a multiple of 32768
   const uint64_t window = (uint64_t)kMaxMatchOffset;
-  uint64_t chunk_end = (r->pos / window + 1) * window;
+  const uint64_t D = r->dict.size() % window;
+  uint64_t chunk_end = ((r->pos + D) / window + 1) * window - D;
   if (chunk_end > r->total) chunk_end = r->total;
   uint64_t k = chunk_end - r->pos;
   if (k > n) k = n;
@@ -1319,7 +1338,7 @@ extern "C" uint64_t fb200_reader_read(fb200_reader *r, uint8_t *buf, uint64_t n,
   r->pos += k;
   *status = -1;
   // the status rides on the read that drains the final, partial window flush (inflate.mbt:392-396)
-  if (r->pos == r->total && (r->total % window) != 0) {
+  if (r->pos == r->total && ((r->total + D) % window) != 0) {
     *status = r->status;
     if (err_off) *err_off = r->err_off;
   }

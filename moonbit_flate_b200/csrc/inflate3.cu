@@ -771,6 +771,68 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
 
 } // namespace par
 
+// record area of stream i: out capacity / 3 (a match yields >= 3 bytes) + 4
+__global__ void k_rec_off(const uint64_t *out_off, uint64_t *rec_off, uint64_t ns)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= ns) rec_off[i] = (out_off[i] - out_off[0]) / 3 + 4 * i;
+}
+
+void launch_rec_off(const uint64_t *out_off, uint64_t *rec_off, uint64_t ns, cudaStream_t st)
+{
+  k_rec_off<<<(unsigned)((ns + 1 + 255) / 256), 256, 0, st>>>(out_off, rec_off, ns);
+}
+
+// Stream order for the decode kernel: a counting sort on the compressed size (256-byte classes), largest
+// first.  A warp waits for its slowest stream and runs the union of its lanes' paths, so streams of similar
+// size (similar symbol counts, similar literal / match mix) belong in the same warp, and the long ones
+// should start first.
+constexpr int kOrderBuckets = 1024;
+
+__device__ __forceinline__ int order_bucket(uint64_t clen)
+{
+  const uint64_t b = clen >> 8;
+  return (int)(b < (uint64_t)kOrderBuckets - 1 ? b : (uint64_t)kOrderBuckets - 1);
+}
+
+__global__ void k_order_count(InflateJob j, uint32_t *hist)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < j.nstreams) atomicAdd(&hist[order_bucket(j.comp_off[i + 1] - j.comp_off[i])], 1u);
+}
+
+__global__ void __launch_bounds__(kOrderBuckets) k_order_scan(uint32_t *hist)
+{
+  // start of bucket b = number of streams in larger buckets (descending order)
+  __shared__ uint32_t sh[kOrderBuckets];
+  const int t = threadIdx.x;
+  sh[t] = hist[kOrderBuckets - 1 - t];
+  __syncthreads();
+  for (int o = 1; o < kOrderBuckets; o <<= 1) {
+    const uint32_t v = t >= o ? sh[t - o] : 0u;
+    __syncthreads();
+    sh[t] += v;
+    __syncthreads();
+  }
+  hist[kOrderBuckets - 1 - t] = sh[t] - hist[kOrderBuckets - 1 - t]; // exclusive
+}
+
+__global__ void k_order_scatter(InflateJob j, uint32_t *hist, uint32_t *order)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < j.nstreams) order[atomicAdd(&hist[order_bucket(j.comp_off[i + 1] - j.comp_off[i])], 1u)] = (uint32_t)i;
+}
+
+// decode order of device-resident calls
+void launch_stream_order(const InflateJob &j, uint32_t *order_hist, cudaStream_t st)
+{
+  const unsigned gs = (unsigned)((j.nstreams + 255) / 256);
+  cudaMemsetAsync(order_hist, 0, kOrderBuckets * sizeof(uint32_t), st);
+  k_order_count<<<gs, 256, 0, st>>>(j, order_hist);
+  k_order_scan<<<1, kOrderBuckets, 0, st>>>(order_hist);
+  k_order_scatter<<<gs, 256, 0, st>>>(j, order_hist, const_cast<uint32_t *>(j.order));
+}
+
 void launch_inflate3(const InflateJob &j_in, int num_sms, cudaStream_t st)
 {
   if (j_in.nstreams == 0) return;
@@ -815,6 +877,10 @@ void preload_inflate3_kernels()
   cudaFuncGetAttributes(&a, par::k_inflate_par<6>);
   cudaFuncGetAttributes(&a, par::k_inflate_par<8>);
   cudaFuncGetAttributes(&a, par::k_inflate_par<12>);
+  cudaFuncGetAttributes(&a, k_rec_off);
+  cudaFuncGetAttributes(&a, k_order_count);
+  cudaFuncGetAttributes(&a, k_order_scan);
+  cudaFuncGetAttributes(&a, k_order_scatter);
 }
 
 } // namespace fb

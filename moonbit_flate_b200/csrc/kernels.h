@@ -113,7 +113,6 @@ void launch_affine_u64(uint64_t *out, const uint64_t *in, uint64_t cnt, uint64_t
 void preload_parse_kernels();
 void preload_encode_kernels();
 void preload_inflate_kernels();
-void preload_inflate2_kernels();
 
 struct InflateJob {
   const uint8_t *comp;
@@ -133,7 +132,7 @@ struct InflateJob {
   uint32_t *group_done;     // [ngroups]
   volatile uint32_t *group_flag; // [ngroups] mapped pinned host memory
   uint32_t group_streams;   // streams per group
-  // two-kernel fast path (inflate2.cu): recorded back-references
+  // recorded back-references of the fast path
   uint2 *records;           // {dst, len | (dist-1) << 16}
   const uint64_t *rec_off;  // [nstreams+1] record area of each stream
   uint32_t *nrec;           // [nstreams] records written (0: nothing to copy, or stream handed to the exact kernel)
@@ -144,15 +143,12 @@ struct InflateJob {
   // them (dist > hist_size is the reference's only limit, inflate.mbt:677).  Null: no dictionaries.
   const uint32_t *hist0;
 };
-// K6: batched inflate.  fast_v1: warp-per-stream fast kernel (inflate.cu); otherwise the caller has run
-// launch_inflate2 and only the exact kernel runs here, over the fallback list.
-void launch_inflate(const InflateJob &j, int num_sms, bool fast_v1, cudaStream_t st);
-// thread-per-stream decode + warp-per-stream copy replay (inflate2.cu)
-// order_hist: device scratch of 1024 uint32
-void launch_inflate2(const InflateJob &j, int num_sms, uint32_t *order_hist, cudaStream_t st);
-// warp-per-stream, lanes decode one block in parallel (inflate3.cu)
+// K6: batched inflate.  Fast kernel: one warp per stream, the lanes decode one block in parallel (inflate3.cu);
+// the exact kernel (inflate.cu) then re-decodes the streams on the fallback list with the reference's error behaviour.
 void launch_inflate3(const InflateJob &j, int num_sms, cudaStream_t st);
+void launch_inflate_exact(const InflateJob &j, int num_sms, cudaStream_t st);
 void preload_inflate3_kernels();
+// decode order for device-resident calls (largest compressed size first); order_hist: device scratch of 1024 uint32
 void launch_stream_order(const InflateJob &j, uint32_t *order_hist, cudaStream_t st);
 void launch_rec_off(const uint64_t *out_off, uint64_t *rec_off, uint64_t ns, cudaStream_t st);
 

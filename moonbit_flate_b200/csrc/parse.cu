@@ -52,31 +52,11 @@ __global__ void k_init_sched()
 }
 
 constexpr unsigned kFull = 0xffffffffu;
-#ifndef FB_GTAB_PREFETCH
-#define FB_GTAB_PREFETCH 0 // measured: no gain (19.8 vs 19.4 ms per GiB)
-#endif
-constexpr bool kGtabPrefetch = FB_GTAB_PREFETCH != 0;
-// Look-ahead of the post-match batches: the buckets of the 32 positions after this batch are read now (the
-// value is not needed before the batch ends, so the trip is off the critical path) and, when the batch ends,
-// the candidate bytes those entries point at are prefetched; the next batch then finds both of its serial
-// trips (table entry, candidate bytes) in cache.  A stale entry only costs a useless prefetch.
-// 0 off, 1 bucket prefetch to L2 only, 2 bucket read + candidate prefetch to L2, 3 same with candidates to L1
-#ifndef FB_PF
-#define FB_PF 1
-#endif
-// Tagged table entries for single-block streams (experiment): position (16 bits) + 16 more bits of the hash
-// product, so that a candidate whose 4 bytes cannot be equal is rejected without reading the source.
-#ifndef FB_TAGS
-#define FB_TAGS 0
-#endif
+// Look-ahead of the post-match batches of the global-table warps: the buckets the positions FB_PF_DIST bytes
+// ahead hash to are prefetched into L2, so that the next batch's table read is not a trip to DRAM.
 #ifndef FB_PF_DIST
-#define FB_PF_DIST 32 // how far ahead of the batch the bucket prefetch looks; measured: 24 -> 18.77 ms, 32 -> 18.48, 48 -> 18.72, 64 -> 18.80
+#define FB_PF_DIST 32 // measured: 24 -> 18.77 ms, 32 -> 18.48, 48 -> 18.72, 64 -> 18.80
 #endif
-#ifndef FB_WIDE_BATCH
-#define FB_WIDE_BATCH 0 // compiled out by default: it costs 16 registers (= 4 warps per SM) and measured slower
-#endif
-constexpr bool kWideBatch = FB_WIDE_BATCH != 0;
-constexpr int kWideScratch = 1024; // bytes (= entries) per global-table warp
 
 // match_len tail (deflate-fast.mbt:286-307): number of equal bytes of src[s2..] and src[t..], at most a,
 // given that the first `from` already matched.  32 bytes per step; long matches take four steps per
@@ -110,11 +90,8 @@ __device__ __forceinline__ int match_tail(const uint8_t *srcb, int s2, int t, in
   return a;
 }
 
-__device__ __forceinline__ uint32_t tag_of(uint32_t cv) { return ((cv * kHashMul) >> 2) & 0xffffu; }
-
 template <bool MULTI, typename T, bool GTAB>
-__device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table, uint8_t *scratch, int wide,
-                                             const BlockParJob *bp = nullptr)
+__device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *counter, T *table, const BlockParJob *bp = nullptr)
 {
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1;
@@ -193,7 +170,6 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
       int s = 0, next_emit = 0;
       uint32_t ntok = 0;
       bool modeM = false;
-      uint8_t wide_tag = 0;
       int loop_p0 = 0, k0 = 0;
 
       for (;;) {
@@ -209,128 +185,6 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         // byte each lane already holds, the next probe lane is s' - base, lanes
         // skipped by a match are simply not inserted.  (Exactness argument and CPU
         // emulation: tests/hostmodel/hostmodel.cu, fbm_parse_stream_v2.)
-        // ---- wide fast path (global-table warps, single-block streams): 64 positions per batch ----
-        // Two positions per lane (A = base + lane, B = base + 32 + lane) share the two serial trips to
-        // memory a batch costs (table entries, then candidate bytes).  Same rules as the 32-position batch
-        // below; in addition (a) buckets shared between an A and a B position are detected through a small
-        // tagged scratch ("some A position of this batch wrote this slot": conservative), and (b) after a
-        // restart at lane cur the reference probes consecutive positions only up to lane cur + 33 (skip
-        // schedule d_k = k for k <= 32, deflate-fast.mbt:178-187), so hits are looked for in that range only.
-        if (GTAB && !MULTI && kWideBatch && wide && modeM && s + 63 <= s_limit) {
-          const int base = s - 1;
-          const int posA = base + lane, posB = base + 32 + lane;
-          const uint32_t cvA = ld32u(srcb + posA), cvB = ld32u(srcb + posB);
-          if (lane == 0 && posA + 320 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + posA + 320));
-          const uint32_t hA = hash4(cvA), hB = hash4(cvB);
-          T *slotA = table + hA, *slotB = table + hB;
-          const T oldA = *slotA, oldB = *slotB;
-          wide_tag = (uint8_t)(wide_tag == 255 ? 1 : wide_tag + 1);
-          scratch[hA & (kWideScratch - 1)] = wide_tag;
-          __syncwarp();
-          const unsigned confA = __ballot_sync(kFull, (__match_any_sync(kFull, hA) & lt_mask) != 0);
-          const bool crossB = scratch[hB & (kWideScratch - 1)] == wide_tag;
-          const unsigned peersB = __match_any_sync(kFull, hB); // (every lane must take part: no short-circuit)
-          const unsigned confB = __ballot_sync(kFull, crossB || (peersB & lt_mask) != 0);
-          const int candA = (int)oldA, candB = (int)oldB;
-          const bool okA = (uint32_t)(posA - candA - 1) < (uint32_t)kMaxMatchOffset && lane != 0;
-          const bool okB = (uint32_t)(posB - candB - 1) < (uint32_t)kMaxMatchOffset;
-          uint32_t a0, a1, a2, b0, b1, b2;
-          {
-            const uintptr_t ca = (uintptr_t)(srcb + (okA ? candA : posA));
-            const uintptr_t cb = (uintptr_t)(srcb + (okB ? candB : posB));
-            const uint32_t *qa = (const uint32_t *)(ca & ~(uintptr_t)3), *qb = (const uint32_t *)(cb & ~(uintptr_t)3);
-            const uint32_t sa = (uint32_t)(ca & 3) * 8, sb = (uint32_t)(cb & 3) * 8;
-            const uint32_t u0 = __ldg(qa), u1 = __ldg(qa + 1), u2 = __ldg(qa + 2), u3 = __ldg(qa + 3);
-            const uint32_t v0 = __ldg(qb), v1 = __ldg(qb + 1), v2 = __ldg(qb + 2), v3 = __ldg(qb + 3);
-            a0 = __funnelshift_r(u0, u1, sa); a1 = __funnelshift_r(u1, u2, sa); a2 = __funnelshift_r(u2, u3, sa);
-            b0 = __funnelshift_r(v0, v1, sb); b1 = __funnelshift_r(v1, v2, sb); b2 = __funnelshift_r(v2, v3, sb);
-          }
-          // own bytes +4 / +8: A lanes read on into the B positions, B lanes stop at the end of the batch
-          const uint32_t dA4 = __shfl_down_sync(kFull, cvA, 4), dA8 = __shfl_down_sync(kFull, cvA, 8);
-          const uint32_t rB4 = __shfl_sync(kFull, cvB, (lane + 4) & 31), rB8 = __shfl_sync(kFull, cvB, (lane + 8) & 31);
-          const uint32_t pA1 = lane < 28 ? dA4 : rB4, pA2 = lane < 24 ? dA8 : rB8;
-          const uint32_t pB1 = rB4, pB2 = rB8; // valid for lanes <= 27 / <= 23
-          const bool hitA = okA && a0 == cvA, hitB = okB && b0 == cvB;
-          const int availB = lane <= 23 ? 8 : (lane <= 27 ? 4 : 0);
-          int extlA, extlB = 0;
-          {
-            const uint32_t x1 = a1 ^ pA1, x2 = a2 ^ pA2;
-            const int e1 = x1 ? ((__ffs(x1) - 1) >> 3) : 4, e2 = x2 ? ((__ffs(x2) - 1) >> 3) : 4;
-            extlA = e1 < 4 ? e1 : 4 + e2;
-            const uint32_t y1 = b1 ^ pB1, y2 = b2 ^ pB2;
-            const int f1 = y1 ? ((__ffs(y1) - 1) >> 3) : 4, f2 = y2 ? ((__ffs(y2) - 1) >> 3) : 4;
-            if (availB >= 4) extlB = (f1 < 4 || availB == 4) ? f1 : 4 + f2;
-          }
-          const int W = confA ? __ffs(confA) - 1 : (confB ? 32 + __ffs(confB) - 1 : 64);
-          if (W >= 2) {
-            const unsigned long long wmask = W < 64 ? (1ull << W) - 1ull : ~0ull;
-            const unsigned long long hitm =
-                ((unsigned long long)__ballot_sync(kFull, hitA) | ((unsigned long long)__ballot_sync(kFull, hitB) << 32)) & wmask;
-            unsigned long long keep = 0, emit = 0;
-            int extA = extlA, extB = extlB;
-            const int packedA = (extlA << 1) | (extlA == 8 ? 1 : 0);
-            const int packedB = (extlB << 1) | (extlB == availB ? 1 : 0);
-            int cur = 1;
-            bool block_done = false;
-            for (;;) {
-              const unsigned long long below = (1ull << cur) - 1ull;
-              const int lim = W < cur + 34 ? W : cur + 34;
-              const unsigned long long lmask = lim < 64 ? (1ull << lim) - 1ull : ~0ull;
-              const unsigned long long hm = hitm & ~below & lmask;
-              if (hm == 0) { // no hit in the consecutive range: literals up to lim, probing continues there
-                keep |= lmask & ~(below >> 1);
-                emit |= lmask & ~below;
-                next_emit = base + lim;
-                modeM = false; loop_p0 = base + cur + 1; k0 = lim - 1 - cur;
-                break;
-              }
-              const int m = __ffsll((long long)hm) - 1;
-              const unsigned long long upto = (2ull << m) - 1ull;
-              keep |= upto & ~(below >> 1);
-              emit |= upto & ~below; // literals cur..m-1, match at m
-              const int packed = m < 32 ? __shfl_sync(kFull, packedA, m) : __shfl_sync(kFull, packedB, m - 32);
-              int ext = packed >> 1;
-              const int s2 = base + m + 4;
-              if (packed & 1) { // the speculative bytes all matched: keep comparing
-                const int t = (m < 32 ? __shfl_sync(kFull, candA, m) : __shfl_sync(kFull, candB, m - 32)) + 4;
-                int s1 = s2 + kMaxMatchLength - 4;
-                if (s1 > n) s1 = n;
-                ext = match_tail(srcb, s2, t, s1 - s2, ext, lane);
-                if (lane == (m & 31)) { if (m < 32) extA = ext; else extB = ext; }
-              }
-              s = s2 + ext;
-              next_emit = s;
-              if (s >= s_limit) { block_done = true; break; } // :236-238
-              const int ncur = s - base;
-              if (ncur >= W) break; // next batch starts at s (still post-match mode)
-              cur = ncur;
-            }
-            const unsigned emit_lo = (unsigned)emit, emit_hi = (unsigned)(emit >> 32);
-#ifdef FB_PARSE_DEBUG
-            if (ntok + __popc(emit_lo) + __popc(emit_hi) > (uint32_t)n || s > n || (okA && (candA < 0 || candA >= posA)) || (okB && (candB < 0 || candB >= posB)))
-              printf("WIDE BAD st=%u base=%d lane=%d W=%d ntok=%u n=%d s=%d emit=%llx hitm=%llx candA=%d candB=%d posA=%d\n", st32, base, lane, W, ntok, n, s, emit, hitm, candA, candB, posA);
-#endif
-            if ((emit_lo >> lane) & 1u) {
-              uint32_t t = cvA & 0xffu; // emit_literal (:273-279)
-              if ((hitm >> lane) & 1ull) // match_token(l + 4 - 3, s - t - 1) (:228-233)
-                t = kMatchType + ((uint32_t)(extA + 1) << kLengthShift) + (uint32_t)(posA - candA - 1);
-              __stcs(&tok[ntok + (uint32_t)__popc(emit_lo & lt_mask)], t);
-            }
-            if ((emit_hi >> lane) & 1u) {
-              uint32_t t = cvB & 0xffu;
-              if ((hitm >> (32 + lane)) & 1ull)
-                t = kMatchType + ((uint32_t)(extB + 1) << kLengthShift) + (uint32_t)(posB - candB - 1);
-              __stcs(&tok[ntok + (uint32_t)__popc(emit_lo) + (uint32_t)__popc(emit_hi & lt_mask)], t);
-            }
-            ntok += (uint32_t)(__popc(emit_lo) + __popc(emit_hi));
-            if ((keep >> lane) & 1ull) *slotA = (T)posA; // kept positions share no bucket
-            if ((keep >> (32 + lane)) & 1ull) *slotB = (T)posB;
-            __syncwarp();
-            if (block_done) break;
-            continue;
-          }
-          __syncwarp();
-        }
         if (modeM && s + 31 <= s_limit) {
           const int base = s - 1;
           const int pos = base + lane;
@@ -340,25 +194,12 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           const uint32_t h = hash4(cv);
           T *slot = table + h;
           const T old = *slot; // (ld.global.cg for the global tables: measured, no difference)
-          const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)((FB_TAGS ? (tag_of(cv) << 16) : 0u) | (uint32_t)pos);
-          T la_old = 0;
-          bool la_ok = false;
-          if (FB_PF && !MULTI && pos + FB_PF_DIST + 4 <= n) {
-            const uint32_t hn = hash4(ld32u(srcb + pos + FB_PF_DIST));
-            if (FB_PF == 1) {
-              if (GTAB) asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hn));
-            } else {
-              la_old = table[hn];
-              la_ok = true;
-            }
-          }
+          const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
+          if (GTAB && !MULTI && pos + FB_PF_DIST + 4 <= n)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hash4(ld32u(srcb + pos + FB_PF_DIST))));
           unsigned conf;
           if (GTAB) { // table in global memory: no dependent read-back, compare buckets across lanes instead
             conf = __ballot_sync(kFull, (__match_any_sync(kFull, h) & lt_mask) != 0);
-            // the buckets of the next 32 positions are very likely needed by the next batch(es): pull them
-            // into L1 now, so that the table read above is not a second serial trip to L2 / DRAM
-            if (kGtabPrefetch && pos + 32 + 8 <= s_limit)
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(table + hash4(ld32u(srcb + pos + 32))));
           } else {
             __syncwarp();
             *slot = mine;
@@ -372,7 +213,6 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           } else {
             cand = (int)((uint32_t)old & 0xffffu);
             ok = (uint32_t)(pos - cand - 1) < (uint32_t)kMaxMatchOffset;
-            if (FB_TAGS) ok = ok && (((uint32_t)old >> 16) == tag_of(cv)); // different tag: the 4 bytes differ
           }
           ok = ok && (lane != 0);
           // 12 bytes at the candidate (own position when there is none: harmless L1 hit)
@@ -459,10 +299,6 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
             ntok += (uint32_t)__popc(emit);
             if (!GTAB) __syncwarp();
             if ((keep >> lane) & 1u) *slot = mine; // kept lanes share no bucket
-            if (FB_PF >= 2 && la_ok && (uint32_t)(pos + 32 - (int)la_old - 1) < (uint32_t)kMaxMatchOffset) {
-              if (FB_PF == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(srcb + (int)la_old));
-              else asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + (int)la_old));
-            }
             __syncwarp();
             if (block_done) break;
             continue;
@@ -514,7 +350,6 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
           cand = (int)((uint32_t)old & 0xffffu);
           const int D = pos - cand;
           ok = (D >= 1) && (D <= kMaxMatchOffset);
-          if (FB_TAGS) ok = ok && (((uint32_t)old >> 16) == tag_of(cv));
         }
         bool hit = false;
         if (active && probe && ok) hit = (ld32u(srcb + cand) == cv); // :196
@@ -526,7 +361,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         const bool committed = active && ((cmask >> lane) & 1u);
         const unsigned cm = __ballot_sync(kFull, committed);
         if (committed && (peers & cm & gt_mask) == 0) // last writer of this bucket in program order
-          table[h] = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)((FB_TAGS ? (tag_of(cv) << 16) : 0u) | (uint32_t)pos);
+          table[h] = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
         __syncwarp();
 
         if (m == 32) { // 32 misses: keep probing (:198-199)
@@ -593,19 +428,17 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
 // (the kernel is latency bound and shared memory caps it at 7 tables per SM)
 // keep theirs in a global scratch area that stays L2 resident.
 template <bool MULTI>
-__global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *gtables, int wide)
+__global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *gtables)
 {
-  using T = typename std::conditional<MULTI || FB_TAGS, uint32_t, uint16_t>::type;
+  using T = typename std::conditional<MULTI, uint32_t, uint16_t>::type;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   if (warp < smem_warps) {
-    parse_worker<MULTI, T, false>(j, counter, reinterpret_cast<T *>(smem_raw) + (size_t)warp * kTableSize, nullptr, 0);
+    parse_worker<MULTI, T, false>(j, counter, reinterpret_cast<T *>(smem_raw) + (size_t)warp * kTableSize);
   } else {
     const int gw = (int)(blockDim.x >> 5) - smem_warps;
     T *table = reinterpret_cast<T *>(gtables) + ((size_t)blockIdx.x * gw + (warp - smem_warps)) * kTableSize;
-    // per-warp bucket scratch of the 64-position batches, behind the shared-memory tables
-    uint8_t *scratch = smem_raw + (size_t)smem_warps * kTableSize * sizeof(T) + (size_t)(warp - smem_warps) * kWideScratch;
-    parse_worker<MULTI, T, true>(j, counter, table, scratch, wide);
+    parse_worker<MULTI, T, true>(j, counter, table);
   }
 }
 
@@ -616,11 +449,11 @@ __global__ void k_parse_blocks(DeflateJob j, BlockParJob bp, uint32_t *counter, 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   if (warp < smem_warps) {
-    parse_worker<true, uint32_t, false>(j, counter, reinterpret_cast<uint32_t *>(smem_raw) + (size_t)warp * kTableSize, nullptr, 0, &bp);
+    parse_worker<true, uint32_t, false>(j, counter, reinterpret_cast<uint32_t *>(smem_raw) + (size_t)warp * kTableSize, &bp);
   } else {
     const int gw = (int)(blockDim.x >> 5) - smem_warps;
     uint32_t *table = reinterpret_cast<uint32_t *>(gtables) + ((size_t)blockIdx.x * gw + (warp - smem_warps)) * kTableSize;
-    parse_worker<true, uint32_t, true>(j, counter, table, nullptr, 0, &bp);
+    parse_worker<true, uint32_t, true>(j, counter, table, &bp);
   }
 }
 
@@ -661,11 +494,7 @@ __global__ void k_bp_round(DeflateJob j, BlockParJob bp, const uint8_t *chg_prev
 
 void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
 
-// FB200_PARSE_WIDE=1 (in a build with -DFB_WIDE_BATCH=1) enables the 64-position batches of the global-table
-// warps.  Exact (the GPU parity and fuzz tests pass with it), but measured slower than the 32-position batches
-// (21.6 vs 20.0 ms per GiB at 5 + 18 warps): sharing the two memory trips does not pay for the extra work per
-// batch.  Compiled out by default.
-static int g_parse_occ_single = 0, g_parse_occ_multi = 0, g_parse_gwarps = 0, g_parse_wide = 0;
+static int g_parse_occ_single = 0, g_parse_occ_multi = 0, g_parse_gwarps = 0;
 static int g_parse_persist = -1;
 constexpr int kMaxDevices = 64;
 
@@ -700,8 +529,6 @@ static void parse_init(int num_sms)
     if (gw > 32) gw = 32;
     if (w + gw == 0) w = 1;
     if (w + gw > 32) gw = 32 - w; // one CTA per SM, at most 1024 threads
-    if (const char *wd = getenv("FB200_PARSE_WIDE")) g_parse_wide = kWideBatch && atoi(wd) != 0;
-    if (FB_TAGS && w > 3) w = 3; // 64 KB per table
     g_parse_occ_single = w;
     g_parse_occ_multi = w > 3 ? 3 : w;
     g_parse_gwarps = gw;
@@ -710,11 +537,8 @@ static void parse_init(int num_sms)
   static bool attr_set[kMaxDevices] = {}; // function attributes are per device
   const int dev = current_device();
   if (!attr_set[dev]) {
-    const int gw = g_parse_gwarps;
-    cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         g_parse_occ_single * kTableSize * (FB_TAGS ? 4 : 2) + gw * (g_parse_wide ? kWideScratch : 0));
-    cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0));
+    cudaFuncSetAttribute(k_parse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_parse_occ_single * kTableSize * 2);
+    cudaFuncSetAttribute(k_parse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_parse_occ_multi * kTableSize * 4);
     cudaFuncSetAttribute(k_parse_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, g_parse_occ_multi * kTableSize * 4);
     const char *co = getenv("FB200_PARSE_CARVEOUT");
     const int pct = co ? atoi(co) : -1;
@@ -768,8 +592,8 @@ void launch_parse_single(const DeflateJob &j, int num_sms, void *gtables, cudaSt
     av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
   }
-  k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * (FB_TAGS ? 4 : 2) + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
-      j, j.counters + 0, g_parse_occ_single, gtables, g_parse_wide);
+  k_parse<false><<<num_sms, (g_parse_occ_single + gw) * 32, g_parse_occ_single * kTableSize * 2, st>>>(
+      j, j.counters + 0, g_parse_occ_single, gtables);
   if (persist && gw) {
     cudaStreamAttrValue av{};
     av.accessPolicyWindow.num_bytes = 0;
@@ -781,8 +605,8 @@ void launch_parse_multi(const DeflateJob &j, int num_sms, void *gtables, cudaStr
 {
   parse_init(num_sms);
   const int gw = g_parse_gwarps;
-  k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4 + gw * (g_parse_wide ? kWideScratch : 0), st>>>(
-      j, j.counters + 1, g_parse_occ_multi, gtables, g_parse_wide);
+  k_parse<true><<<num_sms, (g_parse_occ_multi + gw) * 32, g_parse_occ_multi * kTableSize * 4, st>>>(
+      j, j.counters + 1, g_parse_occ_multi, gtables);
 }
 
 void launch_parse(const DeflateJob &j, int num_sms, void *gtables, cudaStream_t st)

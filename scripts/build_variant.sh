@@ -7,7 +7,7 @@ name=$1; shift
 out=../variants; mkdir -p $out/obj_$name
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in api parse encode inflate inflate2 inflate3; do
+for f in api parse encode inflate inflate3; do
   $NVCC $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC "$@" -c -o $out/obj_$name/$f.o $f.cu &
 done
 wait

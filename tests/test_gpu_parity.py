@@ -459,6 +459,71 @@ def test_reader_preset_dictionary(ctx, oracle, corpus):
         assert r.read_all() == (b"plain stream, no dictionary", None)
 
 
+def _oracle_read_sequence(oracle, comp: bytes, dict_: bytes, want: int):
+    """(bytes, status) of every orc_reader_read(want) call until a status arrives."""
+    import ctypes as C
+
+    a = np.frombuffer(comp, dtype=np.uint8)
+    d = np.frombuffer(dict_, dtype=np.uint8)
+    r = C.c_void_p(oracle.L.orc_reader_new_dict(a.ctypes.data if len(comp) else None, len(comp),
+                                                d.ctypes.data if len(dict_) else None, len(dict_)))
+    buf = np.empty(max(want, 1), np.uint8)
+    seq = []
+    st, eo = C.c_int(-1), C.c_int64(0)
+    while st.value < 0:
+        k = oracle.L.orc_reader_read(r, buf.ctypes.data, want, C.byref(st), C.byref(eo))
+        seq.append((buf[:k].tobytes(), 0 if st.value == 5 else st.value, eo.value if st.value == 1 else 0))
+    oracle.L.orc_reader_free(r)
+    return seq
+
+
+def _gpu_read_sequence(ctx, comp: bytes, dict_: bytes, want: int):
+    import ctypes as C
+    import moonbit_flate_b200 as fb
+
+    r = fb.Reader.new_dict(comp, dict_, ctx) if dict_ else fb.Reader.new(comp, ctx)
+    buf = np.empty(max(want, 1), np.uint8)
+    seq = []
+    st, eo = C.c_int32(-1), C.c_int64(0)
+    while st.value < 0:
+        k = fb._lib.fb200_reader_read(r._h, buf.ctypes.data, want, C.byref(st), C.byref(eo))
+        stv = 0 if st.value == fb.ST_EOF_AT_REFILL else st.value  # the reference reports plain ioeof for both
+        seq.append((buf[: int(k)].tobytes(), stv, eo.value if st.value == 1 else 0))
+    return seq
+
+
+@pytest.mark.parametrize("want", [1 << 20, 32768, 10000])
+def test_reader_read_granularity(ctx, oracle, corpus, want):
+    """Decompressor.read (inflate.mbt:382-407) hands out at most one 32 KiB window flush per call, and the final
+    status rides on the read that drains the last partial flush -- or arrives alone, with 0 bytes, when the output
+    ended exactly on a flush.  With a preset dictionary of D bytes the window starts at wr_pos = D
+    (dict-decoder.mbt:56-62), which shifts every flush boundary.  fb200_reader_read must return the same sequence
+    of (bytes, status) as the oracle's reader: valid streams, exact multiples of the window, corrupt and truncated
+    streams (partial output, then the error), dictionaries of 100 / 5000 / 32768 / 50000 bytes."""
+    cases = []
+    for n in (0, 1, 32767, 32768, 32769, 65536, 100000, 3 * 32768):
+        d = corpus.unit(n, seed=31, index=n, klass=0)
+        cases.append((oracle.deflate(d), b""))
+    big = corpus.unit(150000, seed=32, index=1, klass=0)
+    cbig = oracle.deflate(big)
+    cases.append((cbig[: len(cbig) // 2], b""))                       # truncated: unexpected EOF after partial output
+    bad = bytearray(cbig)
+    bad[len(bad) // 2] ^= 0x55
+    cases.append((bytes(bad), b""))                                   # (most likely) corrupt somewhere in the middle
+    for dlen in (100, 5000, 32768, 50000):
+        dict_ = corpus.unit(dlen, seed=91, index=dlen, klass=0)
+        for n in (70000, 32768 - (dlen % 32768), 65536 - (dlen % 32768), 98304):
+            data = dict_[-3000:] + corpus.unit(n, seed=92, index=dlen, klass=0)
+            data = data[:n] if n >= 3000 else data
+            co = zlib.compressobj(6, zlib.DEFLATED, -15, zdict=dict_)
+            cases.append((co.compress(data) + co.flush(), dict_))
+    for comp, dict_ in cases:
+        want_seq = _oracle_read_sequence(oracle, comp, dict_, want)
+        got_seq = _gpu_read_sequence(ctx, comp, dict_, want)
+        assert [(len(b), s, e) for b, s, e in got_seq] == [(len(b), s, e) for b, s, e in want_seq], (len(comp), len(dict_))
+        assert got_seq == want_seq
+
+
 def test_two_contexts_two_gpus_one_process(oracle, corpus):
     """One context per GPU inside ONE process (the C ABI's contract): device scratch and kernel attributes are
     per context / per device.  Skipped on a single-GPU box."""
@@ -482,3 +547,24 @@ def test_two_contexts_two_gpus_one_process(oracle, corpus):
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("overlap", ["auto", "forced"])
+def test_smoke_with_blocking_launches(overlap):
+    """Tools that make kernel launches synchronous (ncu, compute-sanitizer, cuda-gdb, CUDA_LAUNCH_BLOCKING=1) must
+    not deadlock the host-buffer calls, whose kernels wait on a watermark the H2D copy stream advances: every copy
+    is queued before the kernel is launched, and with such a tool attached the calls copy first and launch after
+    (fb200_ctx::overlap_h2d).  `forced` keeps the watermark overlap on under blocking launches: feed-first alone
+    has to be enough there."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    env.pop("FB200_HOST_OVERLAP", None)
+    if overlap == "forced":
+        env["FB200_HOST_OVERLAP"] = "1"
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
+                       timeout=180, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "smoke ok" in r.stdout
