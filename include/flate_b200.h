@@ -123,6 +123,21 @@ int fb200_inflate_batch_dev(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_
                             int32_t *d_status, int64_t *d_err_off, uint64_t *d_consumed);
 
 /* ------------------------------------------------------------------ */
+/* Asynchronous forms of the host-buffer calls: they return at once, the work runs on a helper thread owned by
+ * the context, and fb200_wait blocks until it has finished and returns its result code.  One call in flight per
+ * context (a second one returns FB200_ERR_ARG); every buffer and result pointer must stay valid until fb200_wait
+ * returns.  Two contexts on one GPU overlap a deflate call with an inflate call: the H2D copy of one travels
+ * beside the D2H copy of the other (PCIe is full duplex) and the kernels of both share the SMs. */
+int fb200_deflate_segments_async(fb200_ctx *ctx, const uint8_t *src, uint64_t n, uint64_t seg_size,
+                                 uint8_t *dst, uint64_t dst_cap, uint64_t *seg_off, uint64_t *out_len);
+int fb200_deflate_streams_async(fb200_ctx *ctx, const uint8_t *src, const uint64_t *src_off, uint64_t nstreams,
+                                uint8_t *dst, uint64_t dst_cap, uint64_t *dst_off, uint64_t *out_len);
+int fb200_inflate_batch_async(fb200_ctx *ctx, const uint8_t *comp, const uint64_t *comp_off, uint64_t nstreams,
+                              uint8_t *out, const uint64_t *out_off, uint64_t *out_len, int32_t *status,
+                              int64_t *err_off, uint64_t *consumed);
+int fb200_wait(fb200_ctx *ctx);
+
+/* ------------------------------------------------------------------ */
 /* Multi-GPU framing helpers (one process per GPU).  The
  * reference defines no container; this frame is an addition:
  *   magic "FB2\0" u32 | seg_size u32 | nseg u64 | comp_size u32[nseg] | streams */

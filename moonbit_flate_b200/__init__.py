@@ -76,6 +76,11 @@ ABI = {
         C.c_int, [C.c_void_p, _u8p, _u64p, C.c_uint64, _u8p, _u64p, _u64p, C.c_void_p, C.c_void_p, _u64p]),
     "fb200_inflate_batch_dev": (
         C.c_int, [C.c_void_p, _u8p, _u64p, C.c_uint64, _u8p, _u64p, _u64p, C.c_void_p, C.c_void_p, _u64p]),
+    "fb200_deflate_segments_async": (C.c_int, [C.c_void_p, _u8p, C.c_uint64, C.c_uint64, _u8p, C.c_uint64, _u64p, _u64p]),
+    "fb200_deflate_streams_async": (C.c_int, [C.c_void_p, _u8p, _u64p, C.c_uint64, _u8p, C.c_uint64, _u64p, _u64p]),
+    "fb200_inflate_batch_async": (
+        C.c_int, [C.c_void_p, _u8p, _u64p, C.c_uint64, _u8p, _u64p, _u64p, C.c_void_p, C.c_void_p, _u64p]),
+    "fb200_wait": (C.c_int, [C.c_void_p]),
     "fb200_frame_header_bytes": (C.c_uint64, [C.c_uint64]),
     "fb200_mg_frame_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),
     "fb200_mg_frame_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -231,6 +236,24 @@ class Context:
                           err_off: int):
         rc = _lib.fb200_inflate_batch(self._h, comp, comp_off, ns, out, out_off, out_len, status, err_off, None)
         self._check(rc, "fb200_inflate_batch")
+
+    # asynchronous forms (fb200_*_async + fb200_wait): raw pointers, the caller keeps the buffers alive
+    def deflate_segments_async_ptr(self, src: int, n: int, seg_size: int, dst: int, dst_cap: int, seg_off: int):
+        self._async_len = C.c_uint64()
+        rc = _lib.fb200_deflate_segments_async(self._h, src, n, seg_size, dst, dst_cap, seg_off,
+                                               C.addressof(self._async_len))
+        self._check(rc, "fb200_deflate_segments_async")
+
+    def inflate_batch_async_ptr(self, comp: int, comp_off: int, ns: int, out: int, out_off: int, out_len: int,
+                                status: int, err_off: int):
+        rc = _lib.fb200_inflate_batch_async(self._h, comp, comp_off, ns, out, out_off, out_len, status, err_off, None)
+        self._check(rc, "fb200_inflate_batch_async")
+
+    def wait(self) -> int:
+        """Joins the asynchronous call in flight; returns the compressed size for a deflate call."""
+        self._check(_lib.fb200_wait(self._h), "fb200_wait")
+        v = getattr(self, "_async_len", None)
+        return int(v.value) if v is not None else 0
 
     # ---------------- introspection ----------------
     def last_stats(self) -> Stats:

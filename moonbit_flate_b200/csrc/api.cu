@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace fb;
@@ -98,6 +99,10 @@ struct fb200_ctx {
   // the watermark included, between passes) need the copies to have finished before the launch, which is what
   // overlap_h2d == false selects: no watermark, the kernel is ordered behind the last chunk.
   bool overlap_h2d = true;
+  // fb200_*_async: the blocking call runs on a helper thread; fb200_wait joins it (one call in flight per context)
+  std::thread worker;
+  bool async_pending = false;
+  int async_rc = FB200_OK;
   uint64_t *pinned = nullptr; // small pinned read-back area
   // last deflate job (for introspection)
   DeflateJob last{};
@@ -228,6 +233,7 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
 extern "C" void fb200_destroy(fb200_ctx *ctx)
 {
   if (!ctx) return;
+  if (ctx->worker.joinable()) ctx->worker.join();
   cudaSetDevice(ctx->device);
   DevBuf *all[] = {&ctx->stream_blk0, &ctx->stream_bytes, &ctx->stream_trailer, &ctx->dst_off_own, &ctx->blk_stream,
                    &ctx->blk_ntok, &ctx->blk_kind, &ctx->blk_bits, &ctx->blk_bit_start, &ctx->blk_hdr_nbits,
@@ -1094,6 +1100,55 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
     fprintf(stderr, "[fb200] inflate host: groups=%llu fed=%.2f first_flag=%.2f last_flag=%.2f kernels_done=%.2f end=%.2f ms\n",
             (unsigned long long)ngroups, t_fed - t0, t_first - t0, t_last - t0, t_kdone - t0, now() - t0);
   return FB200_OK;
+}
+
+// ------------------------------------------------------------------
+// Asynchronous forms of the host-buffer calls.  Deflate and inflate of different batches overlap when they run
+// on two contexts: the H2D copy of one call travels beside the D2H copy of the other (PCIe is full duplex) and
+// the kernels of both share the SMs.  The blocking call needs the host while it runs (it issues the D2H copy of
+// every output group as soon as the device reports its size), so the asynchronous form runs it on a helper
+// thread of the context; buffers and result pointers must stay valid until fb200_wait returns.
+#define ASYNC_BEGIN(ctx)                                                                     \
+  do {                                                                                       \
+    if (!(ctx)) return FB200_ERR_ARG;                                                        \
+    if ((ctx)->async_pending) { (ctx)->err = "an asynchronous call is still in flight: fb200_wait first"; return FB200_ERR_ARG; } \
+    if ((ctx)->worker.joinable()) (ctx)->worker.join();                                      \
+    (ctx)->async_pending = true;                                                             \
+  } while (0)
+
+extern "C" int fb200_deflate_segments_async(fb200_ctx *ctx, const uint8_t *src, uint64_t n, uint64_t seg_size,
+                                            uint8_t *dst, uint64_t dst_cap, uint64_t *seg_off, uint64_t *out_len)
+{
+  ASYNC_BEGIN(ctx);
+  ctx->worker = std::thread([=] { ctx->async_rc = fb200_deflate_segments(ctx, src, n, seg_size, dst, dst_cap, seg_off, out_len); });
+  return FB200_OK;
+}
+
+extern "C" int fb200_deflate_streams_async(fb200_ctx *ctx, const uint8_t *src, const uint64_t *src_off, uint64_t nstreams,
+                                           uint8_t *dst, uint64_t dst_cap, uint64_t *dst_off, uint64_t *out_len)
+{
+  ASYNC_BEGIN(ctx);
+  ctx->worker = std::thread([=] { ctx->async_rc = fb200_deflate_streams(ctx, src, src_off, nstreams, dst, dst_cap, dst_off, out_len); });
+  return FB200_OK;
+}
+
+extern "C" int fb200_inflate_batch_async(fb200_ctx *ctx, const uint8_t *comp, const uint64_t *comp_off, uint64_t nstreams,
+                                         uint8_t *out, const uint64_t *out_off, uint64_t *out_len, int32_t *status,
+                                         int64_t *err_off, uint64_t *consumed)
+{
+  ASYNC_BEGIN(ctx);
+  ctx->worker = std::thread(
+      [=] { ctx->async_rc = fb200_inflate_batch(ctx, comp, comp_off, nstreams, out, out_off, out_len, status, err_off, consumed); });
+  return FB200_OK;
+}
+
+extern "C" int fb200_wait(fb200_ctx *ctx)
+{
+  if (!ctx) return FB200_ERR_ARG;
+  if (!ctx->async_pending) return FB200_OK;
+  if (ctx->worker.joinable()) ctx->worker.join();
+  ctx->async_pending = false;
+  return ctx->async_rc;
 }
 
 // ------------------------------------------------------------------

@@ -120,14 +120,6 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(DeflateJob j)
 void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st, int warps_per_cta)
 {
   if (j.blk_end <= j.blk_begin) return;
-  static bool inited[64] = {}; // function attributes are per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev = dev >= 0 && dev < 64 ? dev : 0;
-  if (!inited[dev]) {
-    cudaFuncSetAttribute(k_build_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildWarps * (int)sizeof(HuffScratch));
-    inited[dev] = true;
-  }
   int w = warps_per_cta;
   if (w < 1) w = 1;
   if (w > kBuildWarps) w = kBuildWarps;
@@ -394,6 +386,8 @@ void launch_zero_range(const DeflateJob &j, cudaStream_t st)
 // deadlock: every kernel of this file is loaded when the context is created.
 void preload_encode_kernels()
 {
+  // function attributes are per device: set when the context is created
+  cudaFuncSetAttribute(k_build_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildWarps * (int)sizeof(HuffScratch));
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_histogram);
   cudaFuncGetAttributes(&a, k_build_codes);

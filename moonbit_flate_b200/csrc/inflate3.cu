@@ -833,25 +833,30 @@ void launch_stream_order(const InflateJob &j, uint32_t *order_hist, cudaStream_t
   k_order_scatter<<<gs, 256, 0, st>>>(j, order_hist, const_cast<uint32_t *>(j.order));
 }
 
+// process-wide launch configuration, read once (preload_inflate3_kernels: when the first context is created)
+static long g_win_kb = -1;
+static int g_minb = 6; // 24 warps per SM at 80 registers: more occupancy only buys spills
+
+static void inflate3_config()
+{
+  static bool done = false;
+  if (done) return;
+  if (const char *e = getenv("FB200_INFLATE_WINDOW_KB")) g_win_kb = atol(e); // first-block window; 0 = no windows at all
+  if (const char *e = getenv("FB200_INFLATE_CTAS")) {
+    const int m = atoi(e);
+    if (m == 4 || m == 5 || m == 6 || m == 8 || m == 12) g_minb = m;
+  }
+  done = true;
+}
+
 void launch_inflate3(const InflateJob &j_in, int num_sms, cudaStream_t st)
 {
   if (j_in.nstreams == 0) return;
   InflateJob j = j_in;
-  {
-    static long win_kb = -2;
-    if (win_kb == -2) {
-      const char *e = getenv("FB200_INFLATE_WINDOW_KB"); // first-block window; 0 = no windows at all
-      win_kb = e ? atol(e) : -1;
-    }
-    if (win_kb == 0) j.window_bits = 0xffffffffu;
-    else if (win_kb > 0) j.window_bits = (uint32_t)(win_kb * 8192);
-  }
-  static int minb = 0;
-  if (!minb) {
-    const char *e = getenv("FB200_INFLATE_CTAS");
-    minb = e ? atoi(e) : 6; // 24 warps per SM at 80 registers: more occupancy only buys spills
-    if (minb != 4 && minb != 5 && minb != 6 && minb != 8 && minb != 12) minb = 6;
-  }
+  inflate3_config();
+  if (g_win_kb == 0) j.window_bits = 0xffffffffu;
+  else if (g_win_kb > 0) j.window_bits = (uint32_t)(g_win_kb * 8192);
+  const int minb = g_minb;
   const uint64_t want = (j.nstreams + par::kWarps - 1) / par::kWarps;
   const uint64_t maxg = (uint64_t)num_sms * minb;
   const unsigned g = (unsigned)(want < maxg ? want : maxg);
@@ -871,6 +876,7 @@ extern "C" void fb200_debug_stepstat(unsigned long long *out)
 
 void preload_inflate3_kernels()
 {
+  inflate3_config();
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, par::k_inflate_par<4>);
   cudaFuncGetAttributes(&a, par::k_inflate_par<5>);

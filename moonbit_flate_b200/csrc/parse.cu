@@ -784,6 +784,7 @@ void launch_gather_u64(uint64_t *out, const uint64_t *in, uint64_t stride, uint6
 // deadlock: every kernel of this file is loaded when the context is created.
 void preload_parse_kernels()
 {
+  parse_init(0); // process-wide launch configuration + per-device function attributes: before any concurrent use
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_init_sched);
   cudaFuncGetAttributes(&a, k_parse<false>);

@@ -389,3 +389,237 @@ extern "C" int64_t fbm_parse_stream_v2(const uint8_t *src, uint64_t L, uint32_t 
   }
   return (int64_t)total;
 }
+
+// ---------------------------------------------------------------------------
+// v3: emulation of the unified fast batch of parse.cu (round 2).  Besides post-match batches (lane 0 =
+// insert(s-1), lane 1 = probe(s), lanes 2.. = a fresh probe loop), a probe loop that is still in its
+// consecutive regime (probe index k <= 32: positions loop_p0 + k, deflate-fast.mbt:178-187) continues as a fast
+// batch as well: lane l = probe k0 + l at base + l, valid while k0 + l <= 32; past that the reference probes
+// every second position, so in the first segment of such a batch hits are only looked for below
+// nc = 33 - k0.  After the first match of a batch a fresh loop starts and the limit is gone (33 positions reach
+// beyond lane 31).  Everything else (conflict-free prefix W, walk, keep / emit masks) is v2's.
+// stats: [0] fast batches, [1] matches taken in fast batches, [2] fast attempts with W < 2, [3] bit 0 = lowest lane
+// of a bucket group wins the speculative insert, [4] generic batches, [5] bytes advanced by fast batches,
+// [6] bytes advanced by generic batches, [7] fast batches entered from a continuing loop
+extern "C" int64_t fbm_parse_stream_v3(const uint8_t *src, uint64_t L, uint32_t *tokens_out, uint64_t tok_cap,
+                                       uint32_t *blk_ntok, uint64_t blk_cap, uint64_t *stats /*[8]*/)
+{
+  const bool MULTI = L >= (uint64_t)kBlockSize + 128;
+  std::vector<uint32_t> table(kTableSize, MULTI ? 0u : 0xffffu);
+  std::vector<uint32_t> sched(512);
+  {
+    uint32_t d = 0;
+    for (int k = 0; k < 512; k++) {
+      sched[k] = d;
+      d = d + 1 + (d >> 5);
+      if (d > (1u << 20)) d = 1u << 20;
+    }
+  }
+  const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < nblk; b++) {
+    if (b >= blk_cap) return -1;
+    blk_ntok[b] = 0;
+    const uint64_t boff = (uint64_t)b * kBlockSize;
+    const int n = (int)((L - boff) < (uint64_t)kBlockSize ? (L - boff) : (uint64_t)kBlockSize);
+    if (n < 128 || L < 128) continue;
+    const uint8_t *srcb = src + boff;
+    uint32_t *tok = tokens_out + total;
+    const uint32_t S0 = (uint32_t)boff;
+    const int s_limit = n - kInputMargin;
+    int s = 0, next_emit = 0;
+    uint32_t ntok = 0;
+    bool modeM = false;
+    int loop_p0 = 0, k0 = 0;
+    auto emit_lits = [&](int a, int e) {
+      for (int i = a; i < e; i++) tok[ntok++] = srcb[i];
+    };
+    auto enc = [&](int pos) -> uint32_t { return MULTI ? (S0 + (uint32_t)pos + 1u) : (uint32_t)(uint16_t)pos; };
+    if (total + (uint64_t)n > tok_cap) return -1;
+    bool done = false;
+    while (!done) {
+      // ------------------------------------------------ fast batch: 32 consecutive positions base .. base + 31
+      const bool contin = !modeM && k0 <= 31;
+      const int base = modeM ? s - 1 : loop_p0 + k0;
+      if ((modeM || contin) && base + 33 <= s_limit) {
+        const int f0 = modeM ? 1 : 0;            // first probing lane (lane 0 of a post-match batch only inserts)
+        const int nc = modeM ? 64 : 33 - k0;     // lanes of the first segment that are probes of the running loop
+        int pos[32], cand[32], extl[32], avail[32];
+        uint32_t cv[32], h[32], old[32];
+        bool hit[32];
+        for (int l = 0; l < 32; l++) {
+          pos[l] = base + l;
+          cv[l] = ld32(srcb + pos[l]);
+          h[l] = hash4(cv[l]);
+          old[l] = table[h[l]];
+        }
+        int W = 32;
+        {
+          const bool lowest_wins = stats ? (stats[3] & 1) != 0 : true;
+          for (int l = 0; l < 32; l++) {
+            bool loser = false;
+            for (int q = 0; q < 32; q++)
+              if (q != l && h[q] == h[l]) {
+                if (lowest_wins ? q < l : q > l) loser = true;
+              }
+            if (loser) { W = l; break; }
+          }
+        }
+        if (W >= 2) {
+          if (stats) { stats[0]++; if (contin) stats[7]++; }
+          const int start_pos = modeM ? s : base;
+          // a generic batch without an event advances the loop but emits nothing (:198-199): catch up
+          if (contin && next_emit < base) { emit_lits(next_emit, base); next_emit = base; }
+          for (int l = 0; l < 32; l++) {
+            bool ok;
+            if (MULTI) {
+              const uint32_t D = enc(pos[l]) - old[l];
+              ok = old[l] != 0 && D <= (uint32_t)kMaxMatchOffset;
+              cand[l] = pos[l] - (int)D;
+            } else {
+              cand[l] = (int)old[l];
+              ok = (uint32_t)(pos[l] - cand[l] - 1) < (uint32_t)kMaxMatchOffset;
+            }
+            hit[l] = l >= f0 && l < W && ok && ld32(srcb + cand[l]) == cv[l];
+            avail[l] = l <= 23 ? 8 : (l <= 27 ? 4 : 0);
+            extl[l] = 0;
+            if (hit[l]) {
+              const int t = cand[l] + 4;
+              if (t < 0) { avail[l] = 99; extl[l] = 0; }
+              else {
+                while (extl[l] < avail[l] && srcb[pos[l] + 4 + extl[l]] == srcb[t + extl[l]]) extl[l]++;
+              }
+            }
+          }
+          uint32_t keep = 0;
+          int cur = f0;
+          bool first = true;
+          for (;;) {
+            const int lim = (first && nc < W) ? nc : W;
+            int m = -1;
+            for (int l = cur; l < lim; l++)
+              if (hit[l]) { m = l; break; }
+            if (m < 0) { // no hit: lanes cur .. lim-1 are inserted literals, the loop goes on at lane lim
+              for (int l = (cur > 0 ? cur - 1 : 0); l < lim; l++) keep |= 1u << l;
+              for (int l = cur; l < lim; l++) tok[ntok++] = cv[l] & 0xff;
+              next_emit = base + lim;
+              if (first && !modeM) { k0 += lim; }             // same loop, lim more probes done
+              else { loop_p0 = base + cur + 1; k0 = lim - 1 - cur; }
+              modeM = false;
+              break;
+            }
+            if (stats) stats[1]++;
+            for (int l = (cur > 0 ? cur - 1 : 0); l <= m; l++) keep |= 1u << l;
+            for (int l = cur; l < m; l++) tok[ntok++] = cv[l] & 0xff;
+            const int s2 = pos[m] + 4, t = cand[m] + 4;
+            int ext = extl[m];
+            if (t >= 0 && ext == avail[m]) {
+              int s1 = s2 + kMaxMatchLength - 4;
+              if (s1 > n) s1 = n;
+              const int a = s1 - s2;
+              while (ext < a && srcb[s2 + ext] == srcb[t + ext]) ext++;
+            }
+            tok[ntok++] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1);
+            s = s2 + ext;
+            next_emit = s;
+            modeM = true;
+            first = false;
+            if (s >= s_limit) { done = true; break; }
+            const int ncur = s - base;
+            if (ncur >= W) break;
+            cur = ncur;
+          }
+          for (int l = 0; l < 32; l++)
+            if ((keep >> l) & 1u) table[h[l]] = enc(pos[l]);
+          if (stats) stats[5] += (uint64_t)((modeM ? s : loop_p0 + (k0 <= 32 ? k0 : 0)) - start_pos);
+          continue;
+        }
+        if (stats) stats[2]++;
+      }
+      // ------------------------------------------------ generic single-event batch (v1)
+      if (stats) stats[4]++;
+      const int gstart = modeM ? s : loop_p0;
+      int pos[32], cand[32];
+      bool probe[32], fail[32], active[32], hit[32];
+      uint32_t cv[32], h[32], old[32];
+      for (int lane = 0; lane < 32; lane++) {
+        int step;
+        bool loopprobe;
+        if (modeM) {
+          if (lane == 0) { pos[lane] = s - 1; step = 0; probe[lane] = false; loopprobe = false; }
+          else if (lane == 1) { pos[lane] = s; step = 0; probe[lane] = true; loopprobe = false; }
+          else { pos[lane] = s + 1 + (lane - 2); step = 1; probe[lane] = true; loopprobe = true; }
+        } else {
+          const int k = k0 + lane;
+          const uint32_t d = k < 32 ? (uint32_t)k : (k < 512 ? sched[k] : (1u << 20));
+          pos[lane] = loop_p0 + (int)d;
+          step = 1 + (int)(d >> 5);
+          probe[lane] = true; loopprobe = true;
+        }
+        fail[lane] = loopprobe && (pos[lane] + step > s_limit);
+        active[lane] = !fail[lane];
+        cv[lane] = 0; h[lane] = 0x10000u | (uint32_t)lane; old[lane] = 0;
+        if (active[lane]) {
+          cv[lane] = ld32(srcb + pos[lane]);
+          h[lane] = hash4(cv[lane]);
+          old[lane] = table[h[lane]];
+        }
+      }
+      unsigned hitm = 0, failm = 0;
+      for (int lane = 0; lane < 32; lane++) {
+        int lower = -1;
+        for (int q = lane - 1; q >= 0; q--)
+          if (h[q] == h[lane]) { lower = q; break; }
+        bool ok;
+        if (lower >= 0) {
+          cand[lane] = pos[lower];
+          ok = (pos[lane] - cand[lane]) <= kMaxMatchOffset;
+        } else if (MULTI) {
+          const uint32_t D = (S0 + (uint32_t)pos[lane] + 1u) - old[lane];
+          ok = (old[lane] != 0) && (D <= (uint32_t)kMaxMatchOffset);
+          cand[lane] = pos[lane] - (int)D;
+        } else {
+          const int D = pos[lane] - (int)old[lane];
+          ok = (D >= 1) && (D <= kMaxMatchOffset);
+          cand[lane] = (int)old[lane];
+        }
+        hit[lane] = active[lane] && probe[lane] && ok && ld32(srcb + cand[lane]) == cv[lane];
+        if (hit[lane]) hitm |= 1u << lane;
+        if (fail[lane]) failm |= 1u << lane;
+      }
+      const unsigned evt = hitm | failm;
+      const int m = evt ? __builtin_ffs((int)evt) - 1 : 32;
+      const bool mhit = evt && ((hitm >> m) & 1u);
+      for (int lane = 0; lane < 32; lane++) {
+        const bool in = (m == 32) || (mhit ? lane <= m : lane < m);
+        if (active[lane] && in) table[h[lane]] = enc(pos[lane]);
+      }
+      if (m == 32) {
+        if (modeM) { modeM = false; loop_p0 = s + 1; k0 = 30; }
+        else k0 += 32;
+        continue;
+      }
+      if (!mhit) break;
+      const int s_hit = pos[m], c = cand[m];
+      emit_lits(next_emit, s_hit);
+      const int s2 = s_hit + 4, t = c + 4;
+      int ext = 0;
+      if (t >= 0) {
+        int s1 = s2 + kMaxMatchLength - 4;
+        if (s1 > n) s1 = n;
+        const int a = s1 - s2;
+        while (ext < a && srcb[s2 + ext] == srcb[t + ext]) ext++;
+      }
+      tok[ntok++] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1);
+      s = s2 + ext;
+      next_emit = s;
+      if (stats) stats[6] += (uint64_t)(s - gstart);
+      if (s >= s_limit) break;
+      modeM = true;
+    }
+    emit_lits(next_emit, n);
+    blk_ntok[b] = ntok;
+    total += ntok;
+  }
+  return (int64_t)total;
+}
