@@ -56,12 +56,10 @@ constexpr unsigned kFull = 0xffffffffu;
 #define FB_PARSE_SW 5  // default warps per SM with a shared-memory table
 #endif
 #ifndef FB_PARSE_GW
-#define FB_PARSE_GW 25 // default warps per SM with a global-memory table
+#define FB_PARSE_GW 23 // default warps per SM with a global-memory table
 #endif
-// Look-ahead of the post-match batches of the global-table warps: the buckets the positions FB_PF_DIST bytes
-// ahead hash to are prefetched into L2, so that the next batch's table read is not a trip to DRAM.
-#ifndef FB_PF_DIST
-#define FB_PF_DIST 32 // measured: 24 -> 18.77 ms, 32 -> 18.48, 48 -> 18.72, 64 -> 18.80
+#ifndef FB_SMEM_WARPS_HIGH
+#define FB_SMEM_WARPS_HIGH 1 // measured: no difference (18.92 vs 19.00 ms per GiB)
 #endif
 
 // match_len tail (deflate-fast.mbt:286-307): number of equal bytes of src[s2..] and src[t..], at most a,
@@ -173,161 +171,226 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
       const uint32_t S0 = (uint32_t)((int64_t)boff - pos_base); // block start relative to the last table reset (MULTI)
       const int s_limit = n - kInputMargin;
 
-      int s = 0, next_emit = 0;
+      // State between steps: `pend` = the insert of position s - 1 after a match is still to be done (:246-251);
+      // (loop_p0, k0) = the running probe loop, whose probe k sits at loop_p0 + d_k with d_k = k for k <= 32
+      // (:178-187).  The probe of s itself right after a match (:252-260) is probe -1 of the loop that starts
+      // at s + 1.
+      int next_emit = 0;
       uint32_t ntok = 0;
-      bool modeM = false;
+      bool pend = false;
       int loop_p0 = 0, k0 = 0;
+      // Fixed windows: the block is cut into windows of 32 consecutive positions [32 w, 32 w + 32) and lane l of
+      // window w always holds position 32 w + l, so everything a window needs can be requested before the window
+      // in front of it has been walked.  Three windows are in flight:
+      //   C (window jc): source bytes, bucket, table entry and the 16 bytes at the candidate -- ready to be walked;
+      //   B (window jb): source bytes, bucket, table entry (the candidate bytes are requested right before C is walked);
+      //   A (window ja): source bytes.
+      // A table entry read that early may be stale by the time its window is walked (an insert of the windows in
+      // between hit the same bucket): when a window becomes C, right after the inserts of the window before it,
+      // the entry is read again (exC); where the two differ the candidate bytes are fetched anew.  Positions only
+      // grow, so equal entries mean nothing was inserted in between.  What is walked is therefore exactly what the
+      // unpipelined walk reads (CPU emulation of the window walk: tests/hostmodel/hostmodel.cu, fbm_parse_stream_v4).
+      const int jfast_max = s_limit >= 33 ? (s_limit - 33) >> 5 : -1; // last window whose 32 positions all probe without the :188 check
+      int jc = -1, jb = -1, ja = -1;
+      uint32_t cvC = 0, hC = 0, oldC = 0, exC = 0, cvB = 0, hB = 0, oldB = 0, cvA = 0;
+      uint32_t wC0 = 0, wC1 = 0, wC2 = 0, wC3 = 0;
+      const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(srcb) & 3u); // alignment of the block start
+      const uint32_t *srcw = reinterpret_cast<const uint32_t *>(srcb - a0);
+
+      // candidate position and "within reach" from a table entry (:194-196)
+      auto decode = [&](int pos, uint32_t old, int &cand) -> bool {
+        if (MULTI) {
+          const uint32_t D = (S0 + (uint32_t)pos + 1u) - old;
+          cand = pos - (int)D;
+          return (old != 0) && (D <= (uint32_t)kMaxMatchOffset);
+        }
+        cand = (int)(old & 0xffffu);
+        return (uint32_t)(pos - cand - 1) < (uint32_t)kMaxMatchOffset;
+      };
+      // the four aligned words that hold the 12 bytes at the candidate (own position when there is none)
+      auto cand_words = [&](int pos, uint32_t old, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
+        int cand;
+        const bool ok = decode(pos, old, cand);
+        const int at = (ok ? cand : pos) + (int)a0; // byte offset from srcw (>= -32768 for MULTI)
+        const uint32_t *q = srcw + (at >> 2);
+        w0 = __ldg(q); w1 = __ldg(q + 1); w2 = __ldg(q + 2); w3 = __ldg(q + 3);
+      };
+// The value has arrived (and the register is no longer the target of a load in flight) once this has executed:
+// the windows that are walked read registers written by these moves only, so the walk never waits on the
+// scoreboard of a load that was issued for a LATER window.
+#define FB_LANDED(x) asm volatile("mov.b32 %0, %0;" : "+r"(x))
 
       for (;;) {
-        // ---- fast path: post-match batch, 32 consecutive positions s-1 .. s+30 ----
-        // lane 0 = insert(s-1), lane 1 = probe(s), lanes 2.. = probes s+1.. (step 1).
-        // One round evaluates every lane: its 4 bytes, bucket, old entry, the 4-byte
-        // verify and up to 8 bytes of speculative match extension.  A speculative
-        // insert + read-back finds W, the width of the lane prefix in which no two
-        // lanes share a bucket (in each sharing group exactly one lane wins the
-        // store; W = lowest losing lane).  For lanes < W the old entry is what
-        // sequential execution reads whichever earlier lanes end up inserted, so the
-        // prefix is consumed match after match from registers: literals are the low
-        // byte each lane already holds, the next probe lane is s' - base, lanes
-        // skipped by a match are simply not inserted.  (Exactness argument and CPU
-        // emulation: tests/hostmodel/hostmodel.cu, fbm_parse_stream_v2.)
-        if (modeM && s + 31 <= s_limit) {
-          const int base = s - 1;
-          const int pos = base + lane;
-          const uint32_t cv = ld32u(srcb + pos);
-          // (never beyond the block: with host-buffer calls the bytes after it may not have arrived yet)
-          if (lane == 0 && pos + 256 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(srcb + pos + 256));
-          const uint32_t h = hash4(cv);
-          T *slot = table + h;
-          const T old = *slot; // (ld.global.cg for the global tables: measured, no difference)
-          const T mine = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos;
-          if (GTAB && !MULTI && pos + FB_PF_DIST + 4 <= n)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hash4(ld32u(srcb + pos + FB_PF_DIST))));
-          unsigned conf;
-          if (GTAB) { // table in global memory: no dependent read-back, compare buckets across lanes instead
-            conf = __ballot_sync(kFull, (__match_any_sync(kFull, h) & lt_mask) != 0);
-          } else {
-            __syncwarp();
-            *slot = mine;
-          }
-          int cand;
-          bool ok;
-          if (MULTI) {
-            const uint32_t D = (uint32_t)mine - (uint32_t)old;
-            ok = (old != 0) && (D <= (uint32_t)kMaxMatchOffset);
-            cand = pos - (int)D;
-          } else {
-            cand = (int)((uint32_t)old & 0xffffu);
-            ok = (uint32_t)(pos - cand - 1) < (uint32_t)kMaxMatchOffset;
-          }
-          ok = ok && (lane != 0);
-          // 12 bytes at the candidate (own position when there is none: harmless L1 hit)
-          uint32_t c0, c1, c2;
-          {
-            const uint8_t *cp = srcb + (ok ? cand : pos);
-            const uintptr_t ca = (uintptr_t)cp;
-            const uint32_t *q = (const uint32_t *)(ca & ~(uintptr_t)3);
-            const uint32_t sh = (uint32_t)(ca & 3) * 8;
-            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
-            c0 = __funnelshift_r(w0, w1, sh);
-            c1 = __funnelshift_r(w1, w2, sh);
-            c2 = __funnelshift_r(w2, w3, sh);
-          }
-          const uint32_t p1 = __shfl_down_sync(kFull, cv, 4); // bytes pos+4 .. pos+7   (lanes <= 27)
-          const uint32_t p2 = __shfl_down_sync(kFull, cv, 8); // bytes pos+8 .. pos+11  (lanes <= 23)
-          const bool hit = ok && (c0 == cv);
-          int avail = lane <= 23 ? 8 : (lane <= 27 ? 4 : 0);
-          int extl = 0;
-          {
-            const uint32_t x1 = c1 ^ p1, x2 = c2 ^ p2;
-            const int e1 = x1 ? ((__ffs(x1) - 1) >> 3) : 4;
-            const int e2 = x2 ? ((__ffs(x2) - 1) >> 3) : 4;
-            if (avail >= 4) extl = (e1 < 4 || avail == 4) ? e1 : 4 + e2;
-            if (cand + 4 < 0) { extl = 0; avail = 99; } // candidate in the previous block: match_len == 0 (D1)
-          }
-          if (!GTAB) {
-            __syncwarp();
-            const T rb = *slot;
-            conf = __ballot_sync(kFull, rb != mine);
-            // final table state is written below: restore every bucket first
-            *slot = old;
-          }
-          unsigned hitm = __ballot_sync(kFull, hit);
-          const int W = conf ? __ffs(conf) - 1 : 32;
-          if (W >= 2) {
-            const unsigned wmask = (W < 32 ? (1u << W) : 0u) - 1u; // lanes below W
-            hitm &= wmask;
-            // Walk the matches of the prefix.  Only masks are updated per match: `keep` = lanes whose
-            // insert happens, `emit` = lanes that produce a token (literal lanes and match lanes);
-            // the tokens themselves are stored once, after the walk, at ntok + rank within `emit`.
-            unsigned keep = 0, emit = 0;
-            int my_ext = extl;
-            int cur = 1;
-            bool block_done = false;
-            const int packed_mine = (extl << 1) | (extl == avail ? 1 : 0);
+        if (k0 <= 31) {
+          int P = pend ? loop_p0 - 2 : loop_p0 + k0; // next position with something to do
+          int jw = P >> 5;
+          if (jw <= jfast_max) {
+            // ---- (re)fill: whatever of windows jw, jw + 1, jw + 2 is not in flight is read here, in place
+            if (jc != jw) {
+              const int pos = (jw << 5) + lane;
+              cvC = ld32u(srcb + pos);
+              hC = hash4(cvC);
+              oldC = (uint32_t)table[hC];
+              exC = oldC;
+              cand_words(pos, oldC, wC0, wC1, wC2, wC3);
+              jc = jw;
+            }
+            if (jb != jw + 1) {
+              jb = -1;
+              if (jw + 1 <= jfast_max) { cvB = ld32u(srcb + (jw << 5) + 32 + lane); hB = hash4(cvB); oldB = (uint32_t)table[hB]; jb = jw + 1; }
+              ja = -1;
+            }
+            if (ja != jw + 2) {
+              ja = -1;
+              if (jw + 2 <= jfast_max) { cvA = ld32u(srcb + (jw << 5) + 64 + lane); ja = jw + 2; }
+            }
+            FB_LANDED(cvC); FB_LANDED(oldC); FB_LANDED(exC); FB_LANDED(wC0); FB_LANDED(wC1); FB_LANDED(wC2); FB_LANDED(wC3);
+            FB_LANDED(cvB); FB_LANDED(oldB); FB_LANDED(cvA);
+            // ---- window after window, as long as the walk runs on into the next one
+            bool leave_block = false;
             for (;;) {
-              const unsigned below = (1u << cur) - 1u;
-              const unsigned hm = hitm & ~below;
-              if (hm == 0) { // no further hit below W: lanes cur..W-1 are literals, probing continues at lane W
-                keep |= wmask & ~(below >> 1);
-                emit |= wmask & ~below;
-                next_emit = base + W;
-                modeM = false; loop_p0 = base + cur + 1; k0 = W - 1 - cur;
+              const int base = jw << 5, cur0 = P & 31;
+              const int pos = base + lane;
+              // the next stage of each window in flight, requested before this window is walked
+              uint32_t wN0 = 0, wN1 = 0, wN2 = 0, wN3 = 0, hN = 0, cvN = 0, oldN = 0;
+              if (jb >= 0) cand_words(pos + 32, oldB, wN0, wN1, wN2, wN3);
+              if (ja >= 0) { hN = hash4(cvA); oldN = (uint32_t)table[hN]; }
+              const bool a_next = jw + 3 <= jfast_max;
+              if (a_next) cvN = ld32u(srcb + pos + 96);
+              if (lane == 0 && (jw & 3) == 0 && base + 2048 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(srcb + base + 2048));
+              // width W of the prefix of the lanes still to do (>= cur0) in which no two lanes share a bucket and no
+              // table entry has gone stale since it was read
+              const unsigned live = ~((1u << cur0) - 1u);
+              const unsigned conf = __ballot_sync(kFull, (__match_any_sync(kFull, hC) & lt_mask & live) != 0 || exC != oldC) & live;
+              const int W = conf ? __ffs(conf) - 1 : 32;
+              if (W < (cur0 + 2 < 32 ? cur0 + 2 : 32)) { // nothing to walk: this window anew (stale entry) or one exact generic step (shared bucket)
+                const bool stale = (__ballot_sync(kFull, exC != oldC) & live & ((2u << cur0) | (1u << cur0))) != 0;
+                jc = -1;
+                if (stale) goto refill_done; // re-enter through the refill
+                goto generic_step;
+              }
+              {
+                int cand;
+                const bool okd = decode(pos, oldC, cand);
+                uint32_t c0, c1, c2;
+                {
+                  const uint32_t sh = ((uint32_t)((okd ? cand : pos) + (int)a0) & 3u) * 8u;
+                  c0 = __funnelshift_r(wC0, wC1, sh);
+                  c1 = __funnelshift_r(wC1, wC2, sh);
+                  c2 = __funnelshift_r(wC2, wC3, sh);
+                }
+                const uint32_t p1 = __shfl_down_sync(kFull, cvC, 4); // bytes pos+4 .. pos+7   (lanes <= 27)
+                const uint32_t p2 = __shfl_down_sync(kFull, cvC, 8); // bytes pos+8 .. pos+11  (lanes <= 23)
+                const bool hit = okd && (c0 == cvC);
+                int avail = lane <= 23 ? 8 : (lane <= 27 ? 4 : 0);
+                int extl = 0;
+                {
+                  const uint32_t x1 = c1 ^ p1, x2 = c2 ^ p2;
+                  const int e1 = x1 ? ((__ffs(x1) - 1) >> 3) : 4;
+                  const int e2 = x2 ? ((__ffs(x2) - 1) >> 3) : 4;
+                  if (avail >= 4) extl = (e1 < 4 || avail == 4) ? e1 : 4 + e2;
+                  if (MULTI && cand + 4 < 0) { extl = 0; avail = 99; } // candidate in the previous block: match_len == 0 (D1)
+                }
+                const unsigned wmask = (W < 32 ? (1u << W) : 0u) - 1u; // lanes below W
+                const unsigned hitm = __ballot_sync(kFull, hit) & wmask;
+                if (!pend && next_emit < P) { // a generic step without an event advances the loop but emits nothing (:198-199)
+                  for (int i = next_emit + lane; i < P; i += 32) __stcs(&tok[ntok + (uint32_t)(i - next_emit)], (uint32_t)__ldg(srcb + i));
+                  ntok += (uint32_t)(P - next_emit);
+                  next_emit = P;
+                }
+                // Walk the matches of the prefix.  Only masks are updated per match: `keep` = lanes whose insert
+                // happens, `emit` = lanes that produce a token (literal lanes and match lanes); the tokens themselves
+                // are stored once, after the walk, at ntok + rank within `emit`.
+                unsigned keep = 0, emit = 0;
+                int my_ext = extl;
+                int cur = cur0;
+                if (pend) { keep = 1u << cur0; cur = cur0 + 1; pend = false; } // insert(s - 1); probe -1 follows
+                const int packed_mine = (extl << 1) | (extl == avail ? 1 : 0);
+                int lim = cur + 33 - k0 < W ? cur + 33 - k0 : W; // until the first match: probes of the running loop only
+                unsigned lmask = (lim < 32 ? (1u << lim) : 0u) - 1u;
+                for (;;) {
+                  const unsigned below = (cur < 32 ? (1u << cur) : 0u) - 1u;
+                  const unsigned hm = hitm & ~below & lmask;
+                  if (hm == 0) { // no further hit below lim: lanes cur..lim-1 are literals, the loop goes on at lane lim
+                    keep |= lmask & ~below;
+                    emit |= lmask & ~below;
+                    if (lim > cur) next_emit = base + lim;
+                    k0 += lim - cur;
+                    break;
+                  }
+                  const int m = __ffs(hm) - 1;
+                  const unsigned upto = (2u << m) - 1u;
+                  keep |= upto & ~below;
+                  emit |= upto & ~below; // literals cur..m-1, match at m
+                  const int packed = __shfl_sync(kFull, packed_mine, m);
+                  int ext = packed >> 1;
+                  const int s2 = base + m + 4;
+                  if (packed & 1) { // the speculative bytes all matched: keep comparing
+                    const int t = __shfl_sync(kFull, cand, m) + 4;
+                    int s1 = s2 + kMaxMatchLength - 4;
+                    if (s1 > n) s1 = n;
+                    ext = match_tail(srcb, s2, t, s1 - s2, ext, lane);
+                    if (lane == m) my_ext = ext;
+                  }
+                  const int s = s2 + ext;
+                  next_emit = s;
+                  loop_p0 = s + 1;
+                  k0 = -1;
+                  if (s >= s_limit) { leave_block = true; break; } // :236-238
+                  const int ncur = s - base;
+                  if (ncur - 1 < W) keep |= 1u << (ncur - 1); // insert(s - 1) lies in this window's prefix
+                  else pend = true;
+                  if (ncur >= W) break;
+                  cur = ncur;
+                  lim = W;
+                  lmask = wmask;
+                }
+                if ((emit >> lane) & 1u) {
+                  uint32_t t = cvC & 0xffu; // emit_literal (:273-279)
+                  if ((hitm >> lane) & 1u) // match_token(l + 4 - 3, s - t - 1) (:228-233)
+                    t = kMatchType + ((uint32_t)(my_ext + 1) << kLengthShift) + (uint32_t)(pos - cand - 1);
+                  __stcs(&tok[ntok + (uint32_t)__popc(emit & lt_mask)], t);
+                }
+                ntok += (uint32_t)__popc(emit);
+                if ((keep >> lane) & 1u) table[hC] = MULTI ? (T)(S0 + (uint32_t)pos + 1u) : (T)pos; // kept lanes share no bucket
+                __syncwarp();
+              }
+              if (leave_block) break;
+              // ---- where the walk goes on
+              if (k0 > 31) break; // the probe loop has left its consecutive regime: generic steps
+              P = pend ? loop_p0 - 2 : loop_p0 + k0;
+              const int jn = P >> 5;
+              if (jn != jw + 1 || jb != jn) { // the rest of this window (its table entries changed), a window further on, or the end
+                if (jn == jw) jc = -1;
                 break;
               }
-              const int m = __ffs(hm) - 1;
-              const unsigned upto = (2u << m) - 1u;
-              keep |= upto & ~(below >> 1);
-              emit |= upto & ~below; // literals cur..m-1, match at m
-              const int packed = __shfl_sync(kFull, packed_mine, m);
-              int ext = packed >> 1;
-              const int s2 = base + m + 4;
-              if (packed & 1) { // the speculative bytes all matched: keep comparing
-                const int t = __shfl_sync(kFull, cand, m) + 4;
-                int s1 = s2 + kMaxMatchLength - 4;
-                if (s1 > n) s1 = n;
-                ext = match_tail(srcb, s2, t, s1 - s2, ext, lane);
-                if (lane == m) my_ext = ext;
-              }
-              s = s2 + ext;
-              next_emit = s;
-              if (s >= s_limit) { block_done = true; break; } // :236-238
-              const int ncur = s - base;
-              if (ncur >= W) break; // next batch starts at s (still post-match mode)
-              cur = ncur;
+              // ---- the pipeline moves on by one window
+              FB_LANDED(wN0); FB_LANDED(wN1); FB_LANDED(wN2); FB_LANDED(wN3); FB_LANDED(oldN); FB_LANDED(cvN);
+              jw = jn;
+              jc = jb; cvC = cvB; hC = hB; oldC = oldB;
+              wC0 = wN0; wC1 = wN1; wC2 = wN2; wC3 = wN3;
+              exC = (uint32_t)table[hC]; // after this window's inserts
+              jb = ja; cvB = cvA; hB = hN; oldB = oldN;
+              ja = a_next ? jw + 2 : -1; cvA = cvN;
             }
-            if ((emit >> lane) & 1u) {
-              uint32_t t = cv & 0xffu; // emit_literal (:273-279)
-              if ((hitm >> lane) & 1u) // match_token(l + 4 - 3, s - t - 1) (:228-233)
-                t = kMatchType + ((uint32_t)(my_ext + 1) << kLengthShift) + (uint32_t)(pos - cand - 1);
-              __stcs(&tok[ntok + (uint32_t)__popc(emit & lt_mask)], t);
-            }
-            ntok += (uint32_t)__popc(emit);
-            if (!GTAB) __syncwarp();
-            if ((keep >> lane) & 1u) *slot = mine; // kept lanes share no bucket
-            __syncwarp();
-            if (block_done) break;
+            if (leave_block) break;
+          refill_done:
             continue;
           }
-          __syncwarp(); // bucket shared by lanes 0/1: resolve this batch exactly below
         }
-        // ---- generic path: lane's table operation in this batch ----
+      generic_step:
+        // ---- generic step: lane's table operation ----
+        jc = -1; // (the step inserts behind the back of window C; B is checked when it becomes C)
         int pos, step;
         bool probe, loopprobe;
-        if (modeM) {
-          if (lane == 0) { // insert(s-1), :246-251
-            pos = s - 1; step = 0; probe = false; loopprobe = false;
-          } else if (lane == 1) { // probe(s), :252-260
-            pos = s; step = 0; probe = true; loopprobe = false;
-          } else { // new probe loop from s+1 with skip = 32, :261-265 -> :178-202
-            pos = s + 1 + (lane - 2); step = 1; probe = true; loopprobe = true;
-          }
-        } else {
-          const int k = k0 + lane;
-          const uint32_t d = k < 32 ? (uint32_t)k : (k < kSchedLen ? g_sched[k] : (1u << 20));
-          pos = loop_p0 + (int)d;
-          step = 1 + (int)(d >> 5);
-          probe = true; loopprobe = true;
+        if (pend && lane == 0) { // insert(s-1), :246-251
+          pos = loop_p0 - 2; step = 0; probe = false; loopprobe = false;
+        } else { // probe(s) (:252-260) = probe -1; the probe loop from s+1 with skip = 32, :261-265 -> :178-202
+          const int k = pend ? lane - 2 : k0 + lane;
+          const int d = k < 32 ? k : (k < kSchedLen ? (int)g_sched[k] : (1 << 20));
+          pos = loop_p0 + d;
+          step = k < 0 ? 0 : 1 + (d >> 5);
+          probe = true; loopprobe = k >= 0;
         }
         const bool fail = loopprobe && (pos + step > s_limit); // :188
         const bool active = !fail;
@@ -348,14 +411,8 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         if (lower) {
           cand = ppos;
           ok = (pos - cand) <= kMaxMatchOffset;
-        } else if (MULTI) {
-          const uint32_t D = (S0 + (uint32_t)pos + 1u) - (uint32_t)old;
-          ok = (old != 0) && (D <= (uint32_t)kMaxMatchOffset);
-          cand = pos - (int)D;
         } else {
-          cand = (int)((uint32_t)old & 0xffffu);
-          const int D = pos - cand;
-          ok = (D >= 1) && (D <= kMaxMatchOffset);
+          ok = decode(pos, old, cand);
         }
         bool hit = false;
         if (active && probe && ok) hit = (ld32u(srcb + cand) == cv); // :196
@@ -371,7 +428,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         __syncwarp();
 
         if (m == 32) { // 32 misses: keep probing (:198-199)
-          if (modeM) { modeM = false; loop_p0 = s + 1; k0 = 30; }
+          if (pend) { pend = false; k0 = 30; } // lanes 1..31 were probes -1..29
           else k0 += 32;
           continue;
         }
@@ -393,10 +450,10 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         if (lane == 0) // match_token(l + 4 - 3, s - t - 1) (:228-233)
           __stcs(&tok[ntok], kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1));
         ntok++;
-        s = s2 + ext;
+        const int s = s2 + ext;
         next_emit = s;
         if (s >= s_limit) break; // :236-238
-        modeM = true;
+        pend = true; loop_p0 = s + 1; k0 = -1;
       }
       // emit_remainder (:152-159)
       for (int i = next_emit + lane; i < n; i += 32) __stcs(&tok[ntok + (uint32_t)(i - next_emit)], (uint32_t)__ldg(srcb + i));
@@ -433,16 +490,28 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
 // Warps [0, smem_warps) of a CTA keep their table in shared memory; the others
 // (the kernel is latency bound and shared memory caps it at 7 tables per SM)
 // keep theirs in a global scratch area that stays L2 resident.
+#ifndef FB_PARSE_LB
+#define FB_PARSE_LB 0 // threads per CTA the register allocation must allow (0: no bound)
+#endif
+#if FB_PARSE_LB
+#define FB_PARSE_BOUNDS __launch_bounds__(FB_PARSE_LB)
+#else
+#define FB_PARSE_BOUNDS
+#endif
+
 template <bool MULTI>
-__global__ void k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *gtables)
+__global__ void FB_PARSE_BOUNDS k_parse(DeflateJob j, uint32_t *counter, int smem_warps, void *gtables)
 {
   using T = typename std::conditional<MULTI, uint32_t, uint16_t>::type;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5;
+  // The warp scheduler prefers the highest warp id among the eligible warps: the shared-memory-table warps, whose
+  // batches have the shortest latency, take the highest ids (FB_SMEM_WARPS_HIGH).
+  const int nw = (int)(blockDim.x >> 5);
+  const int warp = FB_SMEM_WARPS_HIGH ? nw - 1 - (int)(threadIdx.x >> 5) : (int)(threadIdx.x >> 5);
   if (warp < smem_warps) {
     parse_worker<MULTI, T, false>(j, counter, reinterpret_cast<T *>(smem_raw) + (size_t)warp * kTableSize);
   } else {
-    const int gw = (int)(blockDim.x >> 5) - smem_warps;
+    const int gw = nw - smem_warps;
     T *table = reinterpret_cast<T *>(gtables) + ((size_t)blockIdx.x * gw + (warp - smem_warps)) * kTableSize;
     parse_worker<MULTI, T, true>(j, counter, table);
   }

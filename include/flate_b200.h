@@ -161,6 +161,15 @@ int fb200_mg_frame_close(fb200_ctx *ctx, void *d_frame, int owner);
 int fb200_mg_put(fb200_ctx *ctx, void *d_frame, uint64_t offset, const void *d_payload, uint64_t n);
 /* Blocks until every fb200_mg_put of this context has landed. */
 int fb200_mg_wait(fb200_ctx *ctx);
+/* Frame reader (decompress side, SURVEY.md 8e: "scatter compressed ranges, decode locally"): fetches the
+ * compressed streams of segments [first, first + count) from a frame of frame_bytes bytes at d_frame -- on this
+ * GPU, or on the assembling GPU and mapped with fb200_mg_frame_open (then the payload crosses NVLink as one peer
+ * copy) -- into d_comp (device, capacity comp_cap) and writes their offsets, count + 1 values starting at 0, to
+ * the device array d_comp_off: ready for fb200_inflate_batch_dev.  *seg_size / *nseg_total (may be NULL) receive
+ * the header fields, *out_bytes the size of the fetched range.  Returns when the range has arrived. */
+int fb200_mg_get(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint64_t first, uint64_t count,
+                 uint8_t *d_comp, uint64_t comp_cap, uint64_t *d_comp_off, uint32_t *seg_size, uint64_t *nseg_total,
+                 uint64_t *out_bytes);
 
 /* ------------------------------------------------------------------ */
 /* Streaming objects mirroring the reference API (host buffers).       */

@@ -87,6 +87,8 @@ ABI = {
     "fb200_mg_frame_close": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "fb200_mg_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "fb200_mg_wait": (C.c_int, [C.c_void_p]),
+    "fb200_mg_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, C.c_uint64, _u64p,
+                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fb200_writer_new": (C.c_void_p, [C.c_void_p, SINK_FN, C.c_void_p]),
     "fb200_writer_new_dict": (C.c_void_p, [C.c_void_p, SINK_FN, C.c_void_p, _u8p, C.c_uint64]),
     "fb200_writer_write": (C.c_int64, [C.c_void_p, _u8p, C.c_uint64]),
@@ -244,6 +246,11 @@ class Context:
                                                C.addressof(self._async_len))
         self._check(rc, "fb200_deflate_segments_async")
 
+    def deflate_streams_async_ptr(self, src: int, src_off: int, ns: int, dst: int, dst_cap: int, dst_off: int):
+        self._async_len = C.c_uint64()
+        rc = _lib.fb200_deflate_streams_async(self._h, src, src_off, ns, dst, dst_cap, dst_off, C.addressof(self._async_len))
+        self._check(rc, "fb200_deflate_streams_async")
+
     def inflate_batch_async_ptr(self, comp: int, comp_off: int, ns: int, out: int, out_off: int, out_len: int,
                                 status: int, err_off: int):
         rc = _lib.fb200_inflate_batch_async(self._h, comp, comp_off, ns, out, out_off, out_len, status, err_off, None)
@@ -295,6 +302,13 @@ class Context:
 
     def mg_wait(self):
         self._check(_lib.fb200_mg_wait(self._h), "fb200_mg_wait")
+
+    def mg_get(self, d_frame: int, frame_bytes: int, first: int, count: int, d_comp: int, comp_cap: int, d_comp_off: int):
+        """Fetch the streams of segments [first, first + count) from a frame -> (seg_size, nseg_total, bytes)."""
+        seg, nseg, nb = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._check(_lib.fb200_mg_get(self._h, d_frame, frame_bytes, first, count, d_comp, comp_cap, d_comp_off,
+                                      C.byref(seg), C.byref(nseg), C.byref(nb)), "fb200_mg_get")
+        return int(seg.value), int(nseg.value), int(nb.value)
 
     def last_blocks(self, nblocks: int, tok_cap: int):
         ntok = np.zeros(nblocks, np.uint32)

@@ -14,6 +14,8 @@
 #include <chrono>
 #include <cstring>
 #include <new>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -52,6 +54,74 @@ struct DevBuf {
 
 } // namespace
 
+// Host-buffer calls of different contexts on one GPU (the asynchronous forms, or several host threads) are put in
+// FIFO order, by the time of the call, twice over: their H2D input copies follow one another at full PCIe rate
+// instead of sharing the link, and their kernel phases follow one another instead of fighting for the SMs (a
+// persistent parse next to a persistent inflate leaves both crawling) -- while the copies of one call still run
+// beside the kernels and the D2H copies of the others.  A call waits on the host only until its predecessor has
+// QUEUED its phase; the ordering on the device is done with events.
+struct DeviceQueue {
+  std::mutex m;
+  std::condition_variable cv;
+  uint64_t next_ticket = 0, copy_turn = 0, compute_turn = 0;
+  cudaEvent_t last_feed = nullptr, last_compute = nullptr;
+  bool feed_recorded = false, compute_recorded = false;
+};
+static DeviceQueue g_queue[64];
+
+struct QueueTurn { // one host-buffer call's place in its device's queue; releases what it still holds when it dies
+  DeviceQueue *q;
+  uint64_t ticket;
+  bool copy_done = false, compute_done = false;
+  explicit QueueTurn(int device) : q(&g_queue[device >= 0 && device < 64 ? device : 0])
+  {
+    std::lock_guard<std::mutex> lk(q->m);
+    ticket = q->next_ticket++;
+    if (!q->last_feed) {
+      cudaEventCreateWithFlags(&q->last_feed, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&q->last_compute, cudaEventDisableTiming);
+    }
+  }
+  // blocks until every earlier call has queued its input copies; s_in then waits for them on the device
+  void begin_copy(cudaStream_t s_in)
+  {
+    std::unique_lock<std::mutex> lk(q->m);
+    q->cv.wait(lk, [&] { return q->copy_turn == ticket; });
+    if (q->feed_recorded) cudaStreamWaitEvent(s_in, q->last_feed, 0);
+  }
+  void end_copy(cudaStream_t s_in)
+  {
+    std::lock_guard<std::mutex> lk(q->m);
+    if (copy_done) return;
+    if (s_in) { cudaEventRecord(q->last_feed, s_in); q->feed_recorded = true; }
+    copy_done = true;
+    q->copy_turn = ticket + 1;
+    q->cv.notify_all();
+  }
+  void begin_compute(cudaStream_t st)
+  {
+    std::unique_lock<std::mutex> lk(q->m);
+    q->cv.wait(lk, [&] { return q->compute_turn == ticket; });
+    if (q->compute_recorded) cudaStreamWaitEvent(st, q->last_compute, 0);
+  }
+  // st: the stream on which everything this call launched has been (or has been made to be) ordered
+  void end_compute(cudaStream_t st)
+  {
+    std::lock_guard<std::mutex> lk(q->m);
+    if (compute_done) return;
+    if (st) { cudaEventRecord(q->last_compute, st); q->compute_recorded = true; }
+    compute_done = true;
+    q->compute_turn = ticket + 1;
+    q->cv.notify_all();
+  }
+  ~QueueTurn()
+  {
+    // error paths: pass the turns on (in order: a turn can only be passed once it has come)
+    if (!copy_done) { { std::unique_lock<std::mutex> lk(q->m); q->cv.wait(lk, [&] { return q->copy_turn == ticket; }); } end_copy(nullptr); }
+    if (!compute_done) { { std::unique_lock<std::mutex> lk(q->m); q->cv.wait(lk, [&] { return q->compute_turn == ticket; }); } end_compute(nullptr); }
+  }
+};
+
 struct fb200_ctx {
   int device = 0;
   int num_sms = 0;
@@ -72,7 +142,8 @@ struct fb200_ctx {
   DevBuf group_done;
   static constexpr int kMaxChunks = 4096;
   cudaStream_t s_in = nullptr, s_out = nullptr, s_post = nullptr;
-  cudaStream_t s_xfer = nullptr; // fb200_mg_put: peer copies into the frame (copy engines, beside the kernels)
+  cudaStream_t s_xfer = nullptr; // fb200_mg_put / _get: peer copies into / out of the frame (copy engines, beside the kernels)
+  uint64_t *d_frame_res = nullptr; // [2] result of the frame-range kernel
   cudaEvent_t e_xfer = nullptr;
   cudaStream_t s_post2 = nullptr;
   // Group pipeline of the host-buffer deflate (FB200_DEFLATE_PIPELINE, default on): after the parse, K2..K4 run
@@ -209,9 +280,10 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
     cudaEventCreateWithFlags(&ctx->e_out[i], cudaEventDisableTiming);
   }
   cudaMalloc((void **)&ctx->d_wm, 64);
+  cudaMalloc((void **)&ctx->d_frame_res, 16);
   cudaMallocHost((void **)&ctx->wm_vals, fb200_ctx::kMaxChunks * sizeof(uint32_t));
   cudaHostAlloc((void **)&ctx->h_flags, fb200_ctx::kMaxChunks * sizeof(uint32_t), cudaHostAllocMapped);
-  if (!ctx->d_wm || !ctx->wm_vals || !ctx->h_flags) { cudaGetLastError(); fb200_destroy(ctx); return FB200_ERR_CUDA; }
+  if (!ctx->d_wm || !ctx->d_frame_res || !ctx->wm_vals || !ctx->h_flags) { cudaGetLastError(); fb200_destroy(ctx); return FB200_ERR_CUDA; }
   if (const char *e = getenv("FB200_CHUNK_MB")) {
     const long mb = atol(e);
     if (mb > 0) ctx->chunk_bytes = (uint64_t)mb << 20;
@@ -261,6 +333,7 @@ extern "C" void fb200_destroy(fb200_ctx *ctx)
   if (ctx->s_xfer) cudaStreamDestroy(ctx->s_xfer);
   if (ctx->e_xfer) cudaEventDestroy(ctx->e_xfer);
   if (ctx->d_wm) cudaFree(ctx->d_wm);
+  if (ctx->d_frame_res) cudaFree(ctx->d_frame_res);
   if (ctx->wm_vals) cudaFreeHost(ctx->wm_vals);
   if (ctx->h_flags) cudaFreeHost((void *)ctx->h_flags);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -360,6 +433,45 @@ extern "C" int fb200_mg_wait(fb200_ctx *ctx)
   return FB200_OK;
 }
 
+// Frame reader: the compressed streams of segments [first, first + count) travel from the frame (on this GPU, or on
+// the assembling GPU and mapped through CUDA IPC: a peer copy over NVLink) into d_comp, and their offsets
+// (count + 1 values, starting at 0) are written to d_comp_off.  The sizes are read from the frame header by a
+// kernel (peer loads when the frame is remote); the payload moves with the copy engines.
+extern "C" int fb200_mg_get(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint64_t first, uint64_t count,
+                            uint8_t *d_comp, uint64_t comp_cap, uint64_t *d_comp_off, uint32_t *seg_size, uint64_t *nseg_total,
+                            uint64_t *out_bytes)
+{
+  if (!ctx || !d_frame || !d_comp_off || (!d_comp && comp_cap) || !out_bytes) return FB200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->s_xfer;
+  *out_bytes = 0;
+  if (frame_bytes < 16) { ctx->err = "frame shorter than its header"; return FB200_ERR_ARG; }
+  uint32_t *h = reinterpret_cast<uint32_t *>(ctx->pinned + 48);
+  CK(cudaMemcpyAsync(h, d_frame, 16, cudaMemcpyDefault, st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t nseg = (uint64_t)h[2] | ((uint64_t)h[3] << 32);
+  if (h[0] != FB200_FRAME_MAGIC) { ctx->err = "not a frame (magic)"; return FB200_ERR_ARG; }
+  if (fb200_frame_header_bytes(nseg) > frame_bytes || first > nseg || count > nseg - first) {
+    ctx->err = "segment range outside the frame";
+    return FB200_ERR_ARG;
+  }
+  if (seg_size) *seg_size = h[1];
+  if (nseg_total) *nseg_total = nseg;
+  uint64_t *res = ctx->pinned + 50; // {payload offset of segment `first` in the frame, bytes of the range}
+  launch_frame_range(reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(d_frame) + 16), first, count, d_comp_off,
+                     ctx->d_frame_res, st);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(res, ctx->d_frame_res, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t base = fb200_frame_header_bytes(nseg) + res[0], total = res[1];
+  *out_bytes = total;
+  if (base + total > frame_bytes) { ctx->err = "frame truncated: the streams of the range end beyond it"; return FB200_ERR_ARG; }
+  if (total > comp_cap) { ctx->err = "comp_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
+  if (total) CK(cudaMemcpyAsync(d_comp, static_cast<const uint8_t *>(d_frame) + base, total, cudaMemcpyDefault, st));
+  CK(cudaStreamSynchronize(st));
+  return FB200_OK;
+}
+
 // ------------------------------------------------------------------
 // deflate core.  One launch of the parse over the whole batch, then K2, K3, layout and K4.  Device-buffer calls
 // run them over the whole batch in stream order.  Host-buffer calls cut the streams into groups and run K2..K4
@@ -381,6 +493,7 @@ struct DeflateIo {
   uint64_t d_cap = 0;                  // its capacity in bytes
   uint8_t *h_dst = nullptr;            // host-buffer calls: where finished groups are copied to
   uint64_t h_cap = 0;
+  QueueTurn *turn = nullptr;           // host-buffer calls: place in the device's FIFO (kernel phase)
 };
 
 static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
@@ -487,8 +600,9 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
   launches += 1;
   ctx->stage_end(FB200_STAGE_SETUP);
 
-  ctx->stage_begin(FB200_STAGE_PARSE);
   CK(ctx->parse_gtables.ensure(parse_gtables_bytes(ctx->num_sms)));
+  if (io.turn) io.turn->begin_compute(st);
+  ctx->stage_begin(FB200_STAGE_PARSE);
   launch_parse_single(j, ctx->num_sms, ctx->parse_gtables.p, st);
   launches += 1;
   CK(cudaGetLastError());
@@ -542,11 +656,6 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
   }
   ctx->stage_end(FB200_STAGE_PARSE);
 
-  if (parse_uses_l2_persistence()) { // experiment switch: un-pin the tables before anything else runs
-    CK(cudaStreamSynchronize(st));
-    parse_release_l2();
-  }
-
   // K2 .. K4 of one group on stream sp
   auto launch_group = [&](uint64_t g, cudaStream_t sp, bool chain) -> int {
     DeflateJob jg = j;
@@ -590,6 +699,7 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
     if (ngroups) {
       const int rc = launch_group(0, st, false);
       if (rc != FB200_OK) return rc;
+      if (io.turn) io.turn->end_compute(st);
       CK(cudaStreamSynchronize(st));
       if (io.h_dst) {
         const int rc2 = copy_group(0);
@@ -604,6 +714,11 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
     for (uint64_t g = 0; g < ngroups; g++) {
       const int rc = launch_group(g, (g & 1) ? ctx->s_post2 : ctx->s_post, true);
       if (rc != FB200_OK) return rc;
+    }
+    if (io.turn) { // everything this call launches has been queued: the next call's kernels follow the last groups
+      if (ngroups >= 1) CK(cudaStreamWaitEvent(st, ctx->e_gdone[ngroups - 1], 0));
+      if (ngroups >= 2) CK(cudaStreamWaitEvent(st, ctx->e_gdone[ngroups - 2], 0));
+      io.turn->end_compute(st);
     }
     for (uint64_t g = 0; g < ngroups && io.h_dst; g++) {
       CK(cudaEventSynchronize(ctx->e_gsize[g]));
@@ -728,6 +843,7 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
     if (seg_size >= (uint64_t)kBlockSize + 128) { n_multi += full; nmb += full * ((seg_size + kBlockSize - 1) / kBlockSize); }
     if (tail >= (uint64_t)kBlockSize + 128) { n_multi++; nmb += (tail + kBlockSize - 1) / kBlockSize; }
   }
+  QueueTurn turn(ctx->device);
   CK(ctx->p_in[0].ensure(n + 256));
   CK(ctx->p_off_in[0].ensure((ns + 1) * 8));
   CK(ctx->p_off_out[0].ensure((ns + 1) * 8));
@@ -737,6 +853,7 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
   CK(cudaMemsetAsync(ctx->d_wm, 0, 8, st));
   CK(cudaEventRecord(ctx->e_comp[0], st));
   CK(cudaStreamWaitEvent(ctx->s_in, ctx->e_comp[0], 0));
+  turn.begin_copy(ctx->s_in);
   if (src_off) {
     CK(ctx->all_off.ensure((ns + 1) * 8));
     CK(cudaMemcpyAsync(ctx->all_off.p, src_off, (ns + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
@@ -784,6 +901,8 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
       CK(cudaStreamWaitEvent(st, ctx->e_in[1], 0));
     }
   }
+  turn.end_copy(ctx->s_in);
+  io.turn = &turn;
   uint64_t total = 0;
   const int rc = deflate_run(ctx, io, &total);
   *out_len = total;
@@ -1014,6 +1133,8 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
   for (uint64_t g = 0; g < ngroups; g++) ctx->h_flags[g] = 0;
   CK(cudaEventRecord(ctx->e_comp[0], st));
   CK(cudaStreamWaitEvent(ctx->s_in, ctx->e_comp[0], 0));
+  QueueTurn turn(ctx->device);
+  turn.begin_copy(ctx->s_in);
   CK(cudaMemcpyAsync(ctx->all_off.p, comp_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
   CK(cudaMemcpyAsync(ctx->all_off2.p, out_off, (nstreams + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
   CK(cudaEventRecord(ctx->e_in[0], ctx->s_in));
@@ -1053,7 +1174,9 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
       CK(cudaStreamWaitEvent(st, ctx->e_in[1], 0));
     }
   }
+  turn.end_copy(ctx->s_in);
   t_fed = now();
+  turn.begin_compute(st);
   InflateHooks hk;
   hk.avail = ctx->overlap_h2d ? ctx->d_wm + 1 : nullptr;
   hk.group_done = ctx->group_done.as<uint32_t>();
@@ -1063,6 +1186,7 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
                           ctx->p_len[0].as<uint64_t>(), ctx->p_status[0].as<int32_t>(), ctx->p_eoff[0].as<int64_t>(),
                           ctx->p_cons[0].as<uint64_t>(), no, hk);
   if (rc != FB200_OK) return rc;
+  turn.end_compute(st);
   {
     // drain: copy every output group back as soon as the device reports it finished
     for (uint64_t g = 0; g < ngroups; g++) {

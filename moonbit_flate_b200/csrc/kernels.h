@@ -81,9 +81,6 @@ void launch_bp_round(const DeflateJob &j, const BlockParJob &bp, const uint8_t *
                      cudaStream_t st);
 void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *counter, int num_sms, void *gtables,
                          cudaStream_t st);
-// FB200_PARSE_L2PERSIST=1 only: to be called once the parse has completed (un-pins its L2 lines); returns at once otherwise
-void parse_release_l2();
-bool parse_uses_l2_persistence();
 // K2: block kind + histograms (huffman-bit-writer.mbt:550-593, :831)
 void launch_histogram(const DeflateJob &j, cudaStream_t st);
 // K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,
@@ -109,6 +106,11 @@ void launch_fill_seg_off(uint64_t *off, uint64_t nseg, uint64_t seg, uint64_t n,
 
 // out[i] = in[i] + delta (mod 2^64), i in [0, cnt): re-bases offset arrays for chunked host calls
 void launch_affine_u64(uint64_t *out, const uint64_t *in, uint64_t cnt, uint64_t delta, cudaStream_t st);
+
+// frame reader: sizes = the u32 size array of a frame header (device or peer memory).  comp_off[k] = sum of
+// sizes[first .. first + k), k in [0, count]; res[0] = sum of sizes[0 .. first), res[1] = comp_off[count]
+void launch_frame_range(const uint32_t *sizes, uint64_t first, uint64_t count, uint64_t *comp_off, uint64_t *res,
+                        cudaStream_t st);
 
 void preload_parse_kernels();
 void preload_encode_kernels();

@@ -7,7 +7,9 @@ path has no collective: rank r owns the contiguous segment range
 one exchange step is the frame assembly:
 
 1. every rank all-gathers its per-segment compressed sizes (int64, ``nseg_r``
-   entries; NCCL all-gather over NVLink),
+   entries, ragged shards padded for the collective and compacted afterwards, so
+   the header holds the true ``nseg`` entries in segment order; NCCL all-gather
+   over NVLink),
 2. from the gathered sizes every rank derives its payload offset in the frame
    (exclusive scan), and
 3. the payload of every rank lands in GPU 0's frame buffer at that offset.
@@ -16,6 +18,11 @@ one exchange step is the frame assembly:
    copy (copy engines over NVLink, no SM time), so the transfer runs beside the
    rank's next kernels; ``assemble_frame`` is the same exchange with NCCL /
    gloo send/recv (used by the CPU tests and when IPC is unavailable).
+
+The decompress side reads the frame back: ``PeerFrame.get`` (C ABI ``fb200_mg_get``:
+a kernel reads the sizes from the header, one peer copy moves the range) or
+``scatter_frame`` (send/recv) hand every rank the compressed streams of its
+segment range, which it inflates locally.
 
 The frame is an addition -- the reference defines no container:
 ``magic "FB2\\0" u32 | seg_size u32 | nseg u64 | comp_size u32[nseg] | streams``.
@@ -41,45 +48,63 @@ def frame_header_bytes(nseg: int) -> int:
     return 16 + 4 * nseg
 
 
-def gather_sizes(local_sizes: torch.Tensor, world: int) -> torch.Tensor:
-    """All-gather of per-segment compressed sizes.  local_sizes: int64[nseg_local]
-    (equal length on every rank; pad with zeros if the split is ragged).  Returns
-    int64[world, nseg_local]."""
-    out = torch.empty(world * local_sizes.numel(), dtype=local_sizes.dtype, device=local_sizes.device)
+def gather_sizes(local_sizes: torch.Tensor, world: int, nseg_total: Optional[int] = None):
+    """All-gather of per-segment compressed sizes.  local_sizes: int64[nseg_r], the sizes of the segments
+    ``shard_range(nseg_total, world, rank)`` owns (nseg_total defaults to world * nseg_r: equal shards).  Ragged
+    shards are padded to the longest one for the collective and compacted afterwards.  Returns
+    (all_sizes int64[nseg_total] in segment order, totals int64[world] = payload bytes per rank)."""
+    n_loc = int(local_sizes.numel())
+    if nseg_total is None:
+        nseg_total = n_loc * world
+    n_max = (nseg_total + world - 1) // world if world else 0
+    assert n_loc <= n_max, "shard longer than shard_range allows"
+    padded = torch.zeros(n_max, dtype=torch.int64, device=local_sizes.device)
+    padded[:n_loc] = local_sizes.to(torch.int64)
+    out = torch.empty(world * n_max, dtype=torch.int64, device=local_sizes.device)
     if world == 1:
-        out.copy_(local_sizes)
+        out.copy_(padded)
     else:
-        dist.all_gather_into_tensor(out, local_sizes.contiguous())
-    return out.view(world, -1)
+        dist.all_gather_into_tensor(out, padded)
+    out = out.view(world, n_max)
+    totals = out.sum(dim=1)
+    if nseg_total == world * n_max:
+        return out.reshape(-1), totals
+    parts = []
+    for r in range(world):
+        first, last = shard_range(nseg_total, world, r)
+        parts.append(out[r, : last - first])
+    return torch.cat(parts), totals
 
 
-def payload_offsets(all_sizes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """From the gathered sizes: per-rank payload totals and exclusive offsets (int64[world] each)."""
-    totals = all_sizes.sum(dim=1)
-    offs = torch.cumsum(totals, 0) - totals
-    return totals, offs
+def payload_offsets(totals: torch.Tensor) -> torch.Tensor:
+    """Exclusive offsets of the ranks' payloads behind the frame header (int64[world])."""
+    return torch.cumsum(totals, 0) - totals
+
+
+def _frame_header(all_sizes: torch.Tensor, seg_size: int, device) -> torch.Tensor:
+    """magic | seg_size | nseg (u64) | comp_size u32[nseg] as a uint8 tensor on `device`."""
+    nseg = int(all_sizes.numel())
+    assert nseg == 0 or int(all_sizes.max()) < 2 ** 31, "a compressed segment does not fit the u32 size field"
+    head = torch.tensor([FRAME_MAGIC, seg_size, nseg & 0xFFFFFFFF, nseg >> 32], dtype=torch.int64).to(torch.int32)
+    return torch.cat([head.view(torch.uint8).to(device), all_sizes.to(torch.int32).contiguous().view(torch.uint8).to(device)])
 
 
 def assemble_frame(payload: torch.Tensor, local_sizes: torch.Tensor, seg_size: int, rank: int, world: int,
-                   frame: Optional[torch.Tensor]) -> int:
-    """Build the framed output on rank 0.
+                   frame: Optional[torch.Tensor], nseg_total: Optional[int] = None) -> int:
+    """Build the framed output on rank 0 (send/recv transport: gloo on CPU, NCCL when CUDA IPC is unavailable).
 
     payload: uint8[>= sum(local_sizes)] this rank's compacted streams (device on GPU runs);
     frame:   rank 0 only, uint8 buffer large enough for header + all payloads.
     Returns the total frame length (valid on every rank)."""
-    all_sizes = gather_sizes(local_sizes, world)
-    totals, offs = payload_offsets(all_sizes)
+    all_sizes, totals = gather_sizes(local_sizes, world, nseg_total)
     totals_h = totals.cpu().tolist()
-    offs_h = offs.cpu().tolist()
-    nseg = all_sizes.numel()
-    hdr = frame_header_bytes(nseg)
+    offs_h = payload_offsets(totals).cpu().tolist()
+    hdr = frame_header_bytes(int(all_sizes.numel()))
     total = hdr + int(sum(totals_h))
     my_len = int(totals_h[rank])
     if rank == 0:
         assert frame is not None and frame.numel() >= total
-        head = torch.tensor([FRAME_MAGIC, seg_size, nseg & 0xFFFFFFFF, nseg >> 32], dtype=torch.int64).to(torch.int32)
-        frame[:16].copy_(head.view(torch.uint8).to(frame.device))
-        frame[16:hdr].copy_(all_sizes.reshape(-1).to(torch.int32).view(torch.uint8))
+        frame[:hdr].copy_(_frame_header(all_sizes, seg_size, frame.device))
         frame[hdr + offs_h[0]: hdr + offs_h[0] + my_len].copy_(payload[:my_len])
         if world > 1:
             ops = []
@@ -93,6 +118,40 @@ def assemble_frame(payload: torch.Tensor, local_sizes: torch.Tensor, seg_size: i
         for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, payload[:my_len], 0)]):
             w.wait()
     return total
+
+
+def scatter_frame(frame: Optional[torch.Tensor], rank: int, world: int, device=None):
+    """Decompress side with the send/recv transport: rank 0 holds the frame, every rank receives the compressed
+    streams of the segments ``shard_range(nseg, world, rank)`` owns.  Returns (seg_size, nseg, first, sizes int64
+    (cpu), payload uint8) -- sizes and payload of this rank's range."""
+    meta = [None]
+    if rank == 0:
+        seg_size, nseg, sizes, hdr = parse_frame(frame)
+        meta[0] = (seg_size, nseg, sizes.tolist(), hdr)
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0)
+    seg_size, nseg, sizes_l, hdr = meta[0]
+    sizes = torch.tensor(sizes_l, dtype=torch.int64)
+    offs = torch.cumsum(sizes, 0) - sizes
+    first, last = shard_range(nseg, world, rank)
+    mine = int(sizes[first:last].sum())
+    dev = device if device is not None else (frame.device if frame is not None else torch.device("cpu"))
+    payload = torch.empty(mine, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        payload.copy_(frame[hdr + int(offs[first]) if last > first else hdr: (hdr + int(offs[first]) if last > first else hdr) + mine])
+        ops = []
+        for r in range(1, world):
+            f, l = shard_range(nseg, world, r)
+            n = int(sizes[f:l].sum())
+            if n:
+                ops.append(dist.P2POp(dist.isend, frame[hdr + int(offs[f]): hdr + int(offs[f]) + n].contiguous(), r))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+    elif mine:
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, payload, 0)]):
+            w.wait()
+    return seg_size, nseg, first, sizes[first:last], payload
 
 
 class _DevPtr:
@@ -131,11 +190,14 @@ class PeerFrame:
             except Exception as e:  # noqa: BLE001
                 ok = 0
                 self.error = str(e)
+        if not hasattr(self, "error"):
+            self.error = None
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         if world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         self.available = bool(int(flag.item()))
         self._holder = None
+        self.length = 0
         self.view: Optional[torch.Tensor] = None
         if not self.available:
             self.close()
@@ -143,23 +205,27 @@ class PeerFrame:
             self._holder = _DevPtr(self.ptr, self.capacity)
             self.view = torch.as_tensor(self._holder, device=device)
 
-    def put(self, payload: torch.Tensor, local_sizes: torch.Tensor, seg_size: int) -> int:
+    def put(self, payload: torch.Tensor, local_sizes: torch.Tensor, seg_size: int, nseg_total: Optional[int] = None) -> int:
         """payload: this rank's compacted streams (device).  Returns the total frame length."""
-        all_sizes = gather_sizes(local_sizes, self.world)
-        totals, offs = payload_offsets(all_sizes)
+        all_sizes, totals = gather_sizes(local_sizes, self.world, nseg_total)
         totals_h = totals.cpu().tolist()
-        offs_h = offs.cpu().tolist()
-        nseg = all_sizes.numel()
-        hdr = frame_header_bytes(nseg)
+        offs_h = payload_offsets(totals).cpu().tolist()
+        hdr = frame_header_bytes(int(all_sizes.numel()))
         total = hdr + int(sum(totals_h))
         if total > self.capacity:
             raise ValueError(f"frame capacity {self.capacity} < {total}")
         if self.rank == 0:
-            head = torch.tensor([FRAME_MAGIC, seg_size, nseg & 0xFFFFFFFF, nseg >> 32], dtype=torch.int64).to(torch.int32)
-            self.view[:16].copy_(head.view(torch.uint8).to(self.device))
-            self.view[16:hdr].copy_(all_sizes.reshape(-1).to(torch.int32).view(torch.uint8))
+            self.view[:hdr].copy_(_frame_header(all_sizes, seg_size, self.device))
         self.ctx.mg_put(self.ptr, hdr + int(offs_h[self.rank]), payload.data_ptr(), int(totals_h[self.rank]))
+        self.length = total
         return total
+
+    def get(self, first: int, count: int, d_comp: torch.Tensor, d_comp_off: torch.Tensor):
+        """Decompress side: the compressed streams of segments [first, first + count) travel from the frame on
+        rank 0's GPU into d_comp (one peer copy over NVLink), their offsets into d_comp_off (count + 1 int64,
+        starting at 0): ready for fb200_inflate_batch_dev.  Returns (seg_size, nseg_total, bytes)."""
+        return self.ctx.mg_get(self.ptr, self.length, first, count, d_comp.data_ptr(), int(d_comp.numel()),
+                               d_comp_off.data_ptr())
 
     def wait(self):
         self.ctx.mg_wait()

@@ -1663,3 +1663,25 @@ int orc_inflate(const uint8_t *comp, size_t n, uint8_t *out, size_t cap, size_t 
   if (overflow) return ORC_DST_TOO_SMALL;
   return status;
 }
+
+/* Timing helper of bench.py's CPU arm (no reference counterpart): deflate + inflate of streams first, first + stride,
+ * ... of src[off[i] .. off[i+1]) on the calling thread; 1 if every stream round-trips. */
+int orc_codec_pass(const uint8_t *src, const uint64_t *off, uint64_t ns, uint64_t first, uint64_t stride)
+{
+  size_t maxlen = 0;
+  for (uint64_t i = first; i < ns; i += stride)
+    if (off[i + 1] - off[i] > maxlen) maxlen = (size_t)(off[i + 1] - off[i]);
+  const size_t bound = orc_deflate_bound(maxlen);
+  uint8_t *dst = (uint8_t *)malloc(bound ? bound : 1), *out = (uint8_t *)malloc(maxlen + 1);
+  int ok = dst && out;
+  for (uint64_t i = first; ok && i < ns; i += stride) {
+    const size_t n = (size_t)(off[i + 1] - off[i]);
+    const int64_t c = orc_deflate(src + off[i], n, dst, bound);
+    size_t ol = 0;
+    int64_t eo = 0, cons = 0;
+    if (c < 0 || orc_inflate(dst, (size_t)c, out, n, &ol, &eo, &cons) != ORC_OK || ol != n || memcmp(out, src + off[i], n) != 0) ok = 0;
+  }
+  free(dst);
+  free(out);
+  return ok;
+}

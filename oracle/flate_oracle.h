@@ -62,6 +62,8 @@ void orc_writer_free(orc_writer *w);
 int64_t orc_deflate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap);
 /* Upper bound on orc_deflate output for n input bytes. */
 size_t orc_deflate_bound(size_t n);
+/* bench.py timing helper: deflate + inflate of every stride-th stream from `first`; 1 = all round-trip */
+int orc_codec_pass(const uint8_t *src, const uint64_t *off, uint64_t ns, uint64_t first, uint64_t stride);
 
 /* One-shot with per-block introspection.  tokens (may be NULL) receives the
  * concatenated token arrays of every parsed block (deflate-fast.mbt:123-270),

@@ -182,9 +182,9 @@ class HostModel:
         L.fbm_codes.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         L.fbm_parse_stream.restype = C.c_int64
         L.fbm_parse_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
-        L.fbm_parse_stream_v2.restype = C.c_int64
-        L.fbm_parse_stream_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
-                                          C.c_void_p]
+        for fn in (L.fbm_parse_stream_v2, L.fbm_parse_stream_v3, L.fbm_parse_stream_v4):
+            fn.restype = C.c_int64
+            fn.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
 
     def generate(self, freq, max_bits):
         f = np.ascontiguousarray(np.asarray(freq, dtype=np.uint32))
@@ -193,16 +193,21 @@ class HostModel:
         self.L.fbm_generate(f.ctypes.data, f.size, max_bits, lens.ctypes.data, codes.ctypes.data)
         return lens, codes
 
-    def parse_stream(self, data: bytes, v2: bool = False):
+    def parse_stream(self, data: bytes, v2: bool = False, v3: bool = False, v4: bool = False, lowest_wins: bool = True):
+        """v2 / v3 / v4: the multi-match batch / the unified fast batch / the fixed windows of parse.cu; lowest_wins selects which lane of a
+        bucket group wins the speculative insert (arbitrary on the GPU: both extremes must be exact)."""
         n = len(data)
         a = np.frombuffer(data, dtype=np.uint8)
         nb_cap = n // 65535 + 2
         toks = np.zeros(n + 16, np.uint32)
         ntok = np.zeros(nb_cap, np.uint32)
-        if v2:
-            stats = np.zeros(4, np.uint64)
-            tot = self.L.fbm_parse_stream_v2(a.ctypes.data if n else None, n, toks.ctypes.data, n + 16,
-                                             ntok.ctypes.data, nb_cap, stats.ctypes.data)
+        if v2 or v3 or v4:
+            stats = np.zeros(8, np.uint64)
+            stats[3] = 1 if lowest_wins else 0
+            fn = self.L.fbm_parse_stream_v4 if v4 else (self.L.fbm_parse_stream_v3 if v3 else self.L.fbm_parse_stream_v2)
+            tot = fn(a.ctypes.data if n else None, n, toks.ctypes.data, n + 16, ntok.ctypes.data, nb_cap,
+                     stats.ctypes.data)
+            self.last_stats = stats
         else:
             tot = self.L.fbm_parse_stream(a.ctypes.data if n else None, n, toks.ctypes.data, n + 16,
                                           ntok.ctypes.data, nb_cap)

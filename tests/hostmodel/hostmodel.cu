@@ -391,7 +391,8 @@ extern "C" int64_t fbm_parse_stream_v2(const uint8_t *src, uint64_t L, uint32_t 
 }
 
 // ---------------------------------------------------------------------------
-// v3: emulation of the unified fast batch of parse.cu (round 2).  Besides post-match batches (lane 0 =
+// v3: emulation of the unified fast batch (an experiment of round 2, measured and not adopted: experiments/README.md;
+// kept because the model pins the argument the variant rests on).  Besides post-match batches (lane 0 =
 // insert(s-1), lane 1 = probe(s), lanes 2.. = a fresh probe loop), a probe loop that is still in its
 // consecutive regime (probe index k <= 32: positions loop_p0 + k, deflate-fast.mbt:178-187) continues as a fast
 // batch as well: lane l = probe k0 + l at base + l, valid while k0 + l <= 32; past that the reference probes
@@ -616,6 +617,221 @@ extern "C" int64_t fbm_parse_stream_v3(const uint8_t *src, uint64_t L, uint32_t 
       if (stats) stats[6] += (uint64_t)(s - gstart);
       if (s >= s_limit) break;
       modeM = true;
+    }
+    emit_lits(next_emit, n);
+    blk_ntok[b] = ntok;
+    total += ntok;
+  }
+  return (int64_t)total;
+}
+
+// ---------------------------------------------------------------------------
+// v4: emulation of the fixed-window parse (experiments/parse_windows.cu, round 2: measured and not adopted, see
+// experiments/README.md; kept because the model pins the window walk's exactness).  The block is cut into windows of 32
+// consecutive positions [32 j, 32 j + 32); lane l of window j always holds position 32 j + l, so the loads of the
+// next windows can be issued before the current one has been walked (the kernel pipelines them; that changes
+// when values arrive, not which values are used -- stale table entries are detected by a re-read and replaced --
+// so the model reads everything in place).
+//
+// State between windows: `pend` = the insert of position s - 1 after a match is still to be done (:246-251),
+// and the running probe loop (loop_p0, k0): probe k sits at loop_p0 + d_k, d_k = k for k <= 32 (:178-187); the
+// probe of s itself right after a match (:252-260) is probe -1 of the loop that starts at s + 1.  A window is
+// entered at the lane of the next thing to do (cur0); lanes below it lie inside an earlier match: they neither
+// probe nor insert, and they are ignored when the conflict-free lane prefix W is determined.
+extern "C" int64_t fbm_parse_stream_v4(const uint8_t *src, uint64_t L, uint32_t *tokens_out, uint64_t tok_cap,
+                                       uint32_t *blk_ntok, uint64_t blk_cap, uint64_t *stats /*[8]*/)
+{
+  const bool MULTI = L >= (uint64_t)kBlockSize + 128;
+  std::vector<uint32_t> table(kTableSize, MULTI ? 0u : 0xffffu);
+  std::vector<uint32_t> sched(512);
+  {
+    uint32_t d = 0;
+    for (int k = 0; k < 512; k++) {
+      sched[k] = d;
+      d = d + 1 + (d >> 5);
+      if (d > (1u << 20)) d = 1u << 20;
+    }
+  }
+  const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < nblk; b++) {
+    if (b >= blk_cap) return -1;
+    blk_ntok[b] = 0;
+    const uint64_t boff = (uint64_t)b * kBlockSize;
+    const int n = (int)((L - boff) < (uint64_t)kBlockSize ? (L - boff) : (uint64_t)kBlockSize);
+    if (n < 128 || L < 128) continue;
+    const uint8_t *srcb = src + boff;
+    uint32_t *tok = tokens_out + total;
+    const uint32_t S0 = (uint32_t)boff;
+    const int s_limit = n - kInputMargin;
+    int next_emit = 0;
+    uint32_t ntok = 0;
+    bool pend = false;
+    int loop_p0 = 0, k0 = 0;
+    auto emit_lits = [&](int a, int e) {
+      for (int i = a; i < e; i++) tok[ntok++] = srcb[i];
+    };
+    auto enc = [&](int pos) -> uint32_t { return MULTI ? (S0 + (uint32_t)pos + 1u) : (uint32_t)(uint16_t)pos; };
+    auto match_len = [&](int s2, int t) -> int { // :286-342; t < 0 -> 0 (D1)
+      if (t < 0) return 0;
+      int s1 = s2 + kMaxMatchLength - 4;
+      if (s1 > n) s1 = n;
+      int ext = 0;
+      while (s2 + ext < s1 && srcb[s2 + ext] == srcb[t + ext]) ext++;
+      return ext;
+    };
+    if (total + (uint64_t)n > tok_cap) return -1;
+    bool done = false;
+    while (!done) {
+      // ------------------------------------------------ fast window
+      if (k0 <= 31) {
+        const int P = pend ? loop_p0 - 2 : loop_p0 + k0;
+        const int j = P >> 5, base = j << 5, cur0 = P & 31;
+        if (base + 33 <= s_limit) {
+          int pos[32], cand[32];
+          uint32_t cv[32], h[32], old[32];
+          bool hit[32];
+          for (int l = 0; l < 32; l++) {
+            pos[l] = base + l;
+            cv[l] = ld32(srcb + pos[l]);
+            h[l] = hash4(cv[l]);
+            old[l] = table[h[l]];
+          }
+          int W = 32;
+          {
+            const bool lowest_wins = stats ? (stats[3] & 1) != 0 : true;
+            for (int l = cur0; l < 32; l++) {
+              bool loser = false;
+              for (int q = cur0; q < 32; q++)
+                if (q != l && h[q] == h[l]) {
+                  if (lowest_wins ? q < l : q > l) loser = true;
+                }
+              if (loser) { W = l; break; }
+            }
+          }
+          if (W >= (cur0 + 2 < 32 ? cur0 + 2 : 32)) {
+            if (stats) stats[0]++;
+            for (int l = 0; l < 32; l++) {
+              bool ok;
+              if (MULTI) {
+                const uint32_t D = enc(pos[l]) - old[l];
+                ok = old[l] != 0 && D <= (uint32_t)kMaxMatchOffset;
+                cand[l] = pos[l] - (int)D;
+              } else {
+                cand[l] = (int)old[l];
+                ok = (uint32_t)(pos[l] - cand[l] - 1) < (uint32_t)kMaxMatchOffset;
+              }
+              hit[l] = l < W && ok && ld32(srcb + cand[l]) == cv[l];
+            }
+            if (!pend && next_emit < P) { emit_lits(next_emit, P); next_emit = P; }
+            uint32_t keep = 0;
+            int cur = cur0;
+            if (pend) { keep |= 1u << cur0; cur = cur0 + 1; pend = false; } // insert(s - 1); probe -1 follows
+            int lim = cur + 33 - k0 < W ? cur + 33 - k0 : W;               // probes of the running loop only
+            for (;;) {
+              int m = -1;
+              for (int l = cur; l < lim; l++)
+                if (hit[l]) { m = l; break; }
+              if (m < 0) {
+                for (int l = cur; l < lim; l++) { keep |= 1u << l; tok[ntok++] = cv[l] & 0xff; }
+                if (lim > cur) next_emit = base + lim;
+                k0 += lim - cur;
+                break;
+              }
+              if (stats) stats[1]++;
+              for (int l = cur; l <= m; l++) keep |= 1u << l;
+              for (int l = cur; l < m; l++) tok[ntok++] = cv[l] & 0xff;
+              const int s2 = pos[m] + 4, t = cand[m] + 4;
+              const int ext = match_len(s2, t);
+              tok[ntok++] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1);
+              const int s = s2 + ext;
+              next_emit = s;
+              loop_p0 = s + 1;
+              k0 = -1;
+              if (s >= s_limit) { done = true; break; }
+              const int ncur = s - base;
+              if (ncur - 1 < W) keep |= 1u << (ncur - 1); // insert(s - 1) lies in this window's prefix
+              else pend = true;
+              if (ncur >= W) break;
+              cur = ncur;
+              lim = W;
+            }
+            for (int l = 0; l < 32; l++)
+              if ((keep >> l) & 1u) table[h[l]] = enc(pos[l]);
+            continue;
+          }
+          if (stats) stats[2]++;
+        }
+      }
+      // ------------------------------------------------ generic single-event batch
+      if (stats) stats[4]++;
+      int pos[32], cand[32];
+      bool probe[32], fail[32], active[32], hit[32];
+      uint32_t cv[32], h[32], old[32];
+      for (int lane = 0; lane < 32; lane++) {
+        int step;
+        bool loopprobe;
+        if (pend && lane == 0) { pos[lane] = loop_p0 - 2; step = 0; probe[lane] = false; loopprobe = false; }
+        else {
+          const int k = pend ? lane - 2 : k0 + lane;
+          const int d = k < 32 ? k : (k < 512 ? (int)sched[k] : (1 << 20));
+          pos[lane] = loop_p0 + d;
+          step = k < 0 ? 0 : 1 + (d >> 5);
+          probe[lane] = true; loopprobe = k >= 0;
+        }
+        fail[lane] = loopprobe && (pos[lane] + step > s_limit);
+        active[lane] = !fail[lane];
+        cv[lane] = 0; h[lane] = 0x10000u | (uint32_t)lane; old[lane] = 0;
+        if (active[lane]) {
+          cv[lane] = ld32(srcb + pos[lane]);
+          h[lane] = hash4(cv[lane]);
+          old[lane] = table[h[lane]];
+        }
+      }
+      unsigned hitm = 0, failm = 0;
+      for (int lane = 0; lane < 32; lane++) {
+        int lower = -1;
+        for (int q = lane - 1; q >= 0; q--)
+          if (h[q] == h[lane]) { lower = q; break; }
+        bool ok;
+        if (lower >= 0) {
+          cand[lane] = pos[lower];
+          ok = (pos[lane] - cand[lane]) <= kMaxMatchOffset;
+        } else if (MULTI) {
+          const uint32_t D = (S0 + (uint32_t)pos[lane] + 1u) - old[lane];
+          ok = (old[lane] != 0) && (D <= (uint32_t)kMaxMatchOffset);
+          cand[lane] = pos[lane] - (int)D;
+        } else {
+          const int D = pos[lane] - (int)old[lane];
+          ok = (D >= 1) && (D <= kMaxMatchOffset);
+          cand[lane] = (int)old[lane];
+        }
+        hit[lane] = active[lane] && probe[lane] && ok && ld32(srcb + cand[lane]) == cv[lane];
+        if (hit[lane]) hitm |= 1u << lane;
+        if (fail[lane]) failm |= 1u << lane;
+      }
+      const unsigned evt = hitm | failm;
+      const int m = evt ? __builtin_ffs((int)evt) - 1 : 32;
+      const bool mhit = evt && ((hitm >> m) & 1u);
+      for (int lane = 0; lane < 32; lane++) {
+        const bool in = (m == 32) || (mhit ? lane <= m : lane < m);
+        if (active[lane] && in) table[h[lane]] = enc(pos[lane]);
+      }
+      if (m == 32) {
+        if (pend) { pend = false; k0 = 30; } // lanes 1..31 were probes -1..29
+        else k0 += 32;
+        continue;
+      }
+      if (!mhit) break;
+      const int s_hit = pos[m], c = cand[m];
+      emit_lits(next_emit, s_hit);
+      const int s2 = s_hit + 4, t = c + 4;
+      const int ext = match_len(s2, t);
+      tok[ntok++] = kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1);
+      const int s = s2 + ext;
+      next_emit = s;
+      if (s >= s_limit) break;
+      pend = true; loop_p0 = s + 1; k0 = -1;
     }
     emit_lits(next_emit, n);
     blk_ntok[b] = ntok;

@@ -354,6 +354,27 @@ def test_peer_frame_single_rank(ctx, corpus):
     assert (seg_size, n, hdr, total) == (seg, nseg, mg.frame_header_bytes(nseg), hdr + comp.size)
     assert np.array_equal(sizes_f.numpy(), np.diff(off).astype(np.int64))
     assert np.array_equal(pf.view[hdr:total].cpu().numpy(), comp)
+    # the way back (fb200_mg_get): ranges of segments out of the frame, inflated, against the input
+    for first, count in ((0, nseg), (5, 17), (nseg - 1, 1), (nseg, 0), (20, 0)):
+        d_comp = torch.zeros(comp.size + 16, dtype=torch.uint8, device=dev)
+        d_coff = torch.zeros(count + 1, dtype=torch.int64, device=dev)
+        seg_size, n, nbytes = pf.get(first, count, d_comp, d_coff)
+        assert (seg_size, n) == (seg, nseg) and nbytes == int(off[first + count] - off[first])
+        assert np.array_equal(d_coff.cpu().numpy().astype(np.uint64), (off[first: first + count + 1] - off[first]))
+        assert np.array_equal(d_comp[:nbytes].cpu().numpy(), comp[int(off[first]): int(off[first + count])])
+        if count:
+            d_out = torch.zeros(count * seg, dtype=torch.uint8, device=dev)
+            d_ooff = torch.arange(count + 1, dtype=torch.int64, device=dev) * seg
+            d_olen = torch.zeros(count, dtype=torch.int64, device=dev)
+            d_st = torch.zeros(count, dtype=torch.int32, device=dev)
+            d_eo = torch.zeros(count, dtype=torch.int64, device=dev)
+            ctx.inflate_batch_dev(d_comp.data_ptr(), d_coff.data_ptr(), count, d_out.data_ptr(), d_ooff.data_ptr(),
+                                  d_olen.data_ptr(), d_st.data_ptr(), d_eo.data_ptr())
+            assert int(d_st.abs().sum()) == 0
+            assert np.array_equal(d_out.cpu().numpy(), src[first * seg: (first + count) * seg])
+    import moonbit_flate_b200 as fb
+    with pytest.raises(fb.FlateError):
+        pf.get(nseg - 1, 2, torch.zeros(16, dtype=torch.uint8, device=dev), torch.zeros(3, dtype=torch.int64, device=dev))
     pf.close()
 
 

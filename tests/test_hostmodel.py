@@ -111,10 +111,11 @@ def test_batched_parse_model_matches_oracle(hm, oracle, corpus, klass):
     for i, n in enumerate(SIZES):
         d = corpus.unit(n, seed=17, index=i, klass=klass)
         _, wtok, wntok, _, _ = oracle.deflate_ex(d)
-        for v2 in (False, True):
-            toks, ntok = hm.parse_stream(d, v2=v2)
-            assert list(ntok) == list(wntok), (klass, n, v2)
-            assert np.array_equal(toks, wtok), (klass, n, v2)
+        for kw in ({}, {"v2": True}, {"v3": True}, {"v3": True, "lowest_wins": False}, {"v4": True},
+                   {"v4": True, "lowest_wins": False}):
+            toks, ntok = hm.parse_stream(d, **kw)
+            assert list(ntok) == list(wntok), (klass, n, kw)
+            assert np.array_equal(toks, wtok), (klass, n, kw)
 
 
 def _histogram(tokens):
@@ -160,9 +161,11 @@ def test_batched_parse_model_fuzz(hm, oracle):
     rng = np.random.default_rng(7)
     for i, d in enumerate(fuzz_streams(rng, 140)):
         _, wtok, wntok, _, _ = oracle.deflate_ex(d)
-        toks, ntok = hm.parse_stream(d, v2=True)
-        assert list(ntok) == list(wntok), (i, len(d))
-        assert np.array_equal(toks, wtok), (i, len(d))
+        for kw in ({"v2": True}, {"v3": True}, {"v3": True, "lowest_wins": False}, {"v4": True},
+                   {"v4": True, "lowest_wins": False}):
+            toks, ntok = hm.parse_stream(d, **kw)
+            assert list(ntok) == list(wntok), (i, len(d), kw)
+            assert np.array_equal(toks, wtok), (i, len(d), kw)
 
 
 @pytest.mark.parametrize("klass,nblk", [(0, 40), (1, 40), (2, 12), (3, 40), (-1, 60)])

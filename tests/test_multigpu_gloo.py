@@ -36,52 +36,53 @@ def _worker(rank, world, port, nseg_total, outdir):
 
     orc, corpus = Oracle(), Corpus()
     first, last = mg.shard_range(nseg_total, world, rank)
-    nloc_max = (nseg_total + world - 1) // world
     streams = []
     for i in range(first, last):
         streams.append(orc.deflate(corpus.unit(SEG, seed=1, index=i, klass=-1)))
-    sizes = torch.zeros(nloc_max, dtype=torch.int64)
-    sizes[: len(streams)] = torch.tensor([len(s) for s in streams], dtype=torch.int64)
+    sizes = torch.tensor([len(s) for s in streams], dtype=torch.int64)
     payload = torch.from_numpy(np.frombuffer(b"".join(streams) or b"\0", dtype=np.uint8).copy())
     frame = None
     if rank == 0:
-        frame = torch.zeros(mg.frame_header_bytes(nloc_max * world) + world * nloc_max * (SEG + SEG // 8 + 1024),
-                            dtype=torch.uint8)
-    total = mg.assemble_frame(payload, sizes, SEG, rank, world, frame)
+        frame = torch.zeros(mg.frame_header_bytes(nseg_total) + nseg_total * (SEG + SEG // 8 + 1024), dtype=torch.uint8)
+    total = mg.assemble_frame(payload, sizes, SEG, rank, world, frame, nseg_total=nseg_total)
     if rank == 0:
         np.save(os.path.join(outdir, "frame.npy"), frame[:total].numpy())
+    # decompress side: every rank gets the streams of its segment range back out of the frame and inflates them
+    seg_size, nseg, f2, my_sizes, my_payload = mg.scatter_frame(frame[:total] if rank == 0 else None, rank, world)
+    ok = seg_size == SEG and nseg == nseg_total and f2 == first and my_sizes.tolist() == sizes.tolist()
+    pos = 0
+    for k, sz in enumerate(my_sizes.tolist()):
+        st, out, _, cons = orc.inflate(my_payload[pos: pos + sz].numpy().tobytes(), SEG + 1)
+        ok = ok and st == 0 and cons == sz and out == corpus.unit(SEG, seed=1, index=first + k, klass=-1)
+        pos += sz
+    ok = ok and pos == my_payload.numel()
+    open(os.path.join(outdir, f"ok{rank}"), "w").write("1" if ok else "0")
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nseg", [(2, 8), (3, 7)])
-def test_frame_assembly_gloo(tmp_path, world, nseg):
+@pytest.mark.parametrize("world,nseg", [(2, 8), (3, 7), (3, 2)])
+def test_frame_assembly_and_scatter_gloo(tmp_path, world, nseg):
+    """Frame assembly on rank 0 from ragged shards (7 segments over 3 ranks; 2 over 3: one rank owns nothing):
+    the header carries the true segment count and the sizes in segment order (the documented format), the payload
+    is the concatenation of the streams; then the way back: every rank receives its range and inflates it."""
     from moonbit_flate_b200 import multigpu as mg
 
     port = _free_port()
     mp.spawn(_worker, args=(world, port, nseg, str(tmp_path)), nprocs=world, join=True)
     frame = torch.from_numpy(np.load(os.path.join(tmp_path, "frame.npy")))
-    seg_size, n_slots, sizes, hdr = mg.parse_frame(frame)
-    assert seg_size == SEG
+    seg_size, n, sizes, hdr = mg.parse_frame(frame)
+    assert seg_size == SEG and n == nseg and sizes.numel() == nseg and hdr == 16 + 4 * nseg
     orc, corpus = Oracle(), Corpus()
-    # slots: world x ceil(nseg/world); ragged shards leave zero-size slots at the end of a rank's range
-    nloc_max = (nseg + world - 1) // world
-    assert n_slots == nloc_max * world
     pos = hdr
-    seen = 0
+    for i in range(nseg):
+        want = orc.deflate(corpus.unit(SEG, seed=1, index=i, klass=-1))
+        assert int(sizes[i]) == len(want)
+        assert frame[pos: pos + len(want)].numpy().tobytes() == want, i
+        pos += len(want)
+    assert pos == frame.numel()
     for r in range(world):
-        first, last = mg.shard_range(nseg, world, r)
-        for k in range(nloc_max):
-            sz = int(sizes[r * nloc_max + k])
-            if first + k < last:
-                want = orc.deflate(corpus.unit(SEG, seed=1, index=first + k, klass=-1))
-                assert sz == len(want)
-                assert frame[pos: pos + sz].numpy().tobytes() == want, (r, k)
-                seen += 1
-            else:
-                assert sz == 0
-            pos += sz
-    assert seen == nseg and pos == frame.numel()
+        assert open(os.path.join(tmp_path, f"ok{r}")).read() == "1", f"rank {r}: scatter / inflate from the frame"
 
 
 def test_shard_range_partitions():
