@@ -526,26 +526,27 @@ def main():
     # ------------------------------------------------------------------ e2e through the host-buffer C ABI
     e2e = None
     if not args.no_e2e and nbytes <= (3 << 30):
-        # Three contexts: deflate calls alternate between two, inflate calls run on the third, all through the
+        # Four contexts: deflate calls alternate between two, inflate calls between two more, all through the
         # asynchronous form of the host-buffer C ABI (fb200_*_async + fb200_wait).  Two deflate calls are kept in
         # flight -- the input of the second travels while the kernels of the first run -- and inflate call i starts as
         # soon as deflate call i has delivered its streams to (pinned) host memory; the H2D copy of one call travels
         # beside the D2H copy of another (PCIe is full duplex) and the library orders copies and kernel phases of
         # the calls FIFO on the GPU.  The timed region holds K deflate and K inflate calls, fill and drain included.
         ctxD = [ctx, fb.Context(local_rank)]
-        ctxI = fb.Context(local_rank)
+        ctxI = [fb.Context(local_rank), fb.Context(local_rank)]
         ns = nunits
         cap = dc.cap
+        NB = 4  # compressed host buffers: two being written by deflate calls, two being read by inflate calls
         h_off = torch.from_numpy(off.astype(np.int64)).pin_memory()
-        h_dst = [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(3)]
-        h_doff = [torch.zeros(ns + 1, dtype=torch.int64, pin_memory=True) for _ in range(3)]
-        h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        h_out_len = torch.zeros(ns, dtype=torch.int64, pin_memory=True)
-        h_status = torch.zeros(ns, dtype=torch.int32, pin_memory=True)
-        h_err_off = torch.zeros(ns, dtype=torch.int64, pin_memory=True)
+        h_dst = [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(NB)]
+        h_doff = [torch.zeros(ns + 1, dtype=torch.int64, pin_memory=True) for _ in range(NB)]
+        h_out = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        h_out_len = [torch.zeros(ns, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+        h_status = [torch.zeros(ns, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        h_err_off = [torch.zeros(ns, dtype=torch.int64, pin_memory=True) for _ in range(2)]
 
         def deflate_async(i, c=None):
-            b = i % 3
+            b = i % NB
             c = c or ctxD[i & 1]
             if seg:
                 c.deflate_segments_async_ptr(h_src.data_ptr(), nbytes, seg, h_dst[b].data_ptr(), cap, h_doff[b].data_ptr())
@@ -553,25 +554,31 @@ def main():
                 c.deflate_streams_async_ptr(h_src.data_ptr(), h_off.data_ptr(), ns, h_dst[b].data_ptr(), cap, h_doff[b].data_ptr())
 
         def inflate_async(i, c=None):
-            b = i % 3
-            (c or ctxI).inflate_batch_async_ptr(h_dst[b].data_ptr(), h_doff[b].data_ptr(), ns, h_out.data_ptr(),
-                                                h_off.data_ptr(), h_out_len.data_ptr(), h_status.data_ptr(),
-                                                h_err_off.data_ptr())
+            b, o = i % NB, i & 1
+            (c or ctxI[o]).inflate_batch_async_ptr(h_dst[b].data_ptr(), h_doff[b].data_ptr(), ns, h_out[o].data_ptr(),
+                                                   h_off.data_ptr(), h_out_len[o].data_ptr(), h_status[o].data_ptr(),
+                                                   h_err_off[o].data_ptr())
 
         def e2e_run(k):
+            """k deflate + k inflate calls: two deflate calls are kept in flight, inflate call i is issued as soon as
+            deflate call i has returned (its streams are in host memory) and inflate call i - 2 has freed its context."""
             deflate_async(0)
             if k > 1:
                 deflate_async(1)
             cl = 0
             for i in range(k):
                 cl = ctxD[i & 1].wait()
-                if i > 0:
-                    ctxI.wait()
-                inflate_async(i)
                 if i + 2 < k:
                     deflate_async(i + 2)
-            ctxI.wait()
+                if i >= 2:
+                    ctxI[i & 1].wait()
+                inflate_async(i)
+            for c in ctxI:
+                c.wait()
             return cl
+
+        def e2e_ok():
+            return all(int(h_status[o].abs().sum()) == 0 and torch.equal(h_out[o], h_src) for o in range(2))
 
         def e2e_serial_step():
             deflate_async(0, ctx)
@@ -580,10 +587,11 @@ def main():
             ctx.wait()
             return cl
 
-        cl = e2e_run(3)  # warm-up of all contexts + check
-        assert int(h_status.abs().sum()) == 0 and torch.equal(h_out, h_src), "e2e round trip mismatch"
-        h_out.zero_()
-        ksteps = max(3, min(args.steps, 10))
+        cl = e2e_run(4)  # warm-up of all contexts + check
+        assert e2e_ok(), "e2e round trip mismatch"
+        for o in range(2):
+            h_out[o].zero_()
+        ksteps = max(4, min(args.steps, 16))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -591,7 +599,7 @@ def main():
         cl = e2e_run(ksteps)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / ksteps
-        assert int(h_status.abs().sum()) == 0 and torch.equal(h_out, h_src), "e2e round trip mismatch (timed run)"
+        assert e2e_ok(), "e2e round trip mismatch (timed run)"
         # the same two calls one after the other on one context (round-1 definition), for comparison
         e2e_serial_step()
         if world > 1:
@@ -608,8 +616,8 @@ def main():
                "h2d_bytes_per_step": int((nbytes + cl + 3 * meta) * world),
                "d2h_bytes_per_step": int((cl + nbytes + meta + ns * 20) * world),
                "steps": ksteps, "ms_per_step": round(float(t_e[0].item()) * 1e3, 3),
-               "path": "fb200_deflate_*_async (two contexts, alternating) + fb200_inflate_batch_async (third context), "
-                       "pinned host buffers; inflate call i consumes what deflate call i delivered to the host; "
+               "path": "fb200_deflate_*_async on two contexts + fb200_inflate_batch_async on two more, pinned host buffers; "
+                       "inflate call i consumes what deflate call i delivered to the host; two deflate calls in flight; "
                        "pipeline fill and drain inside the timed region",
                "serial": {"value": round(2 * total_unc / float(t_e[1].item()) / 1e9, 3),
                           "ms_per_step": round(float(t_e[1].item()) * 1e3, 3),
@@ -620,7 +628,8 @@ def main():
                 e2e["platform_bound_gbs"] = json.load(open(pb)).get(str(world))
             except Exception:
                 pass
-        ctxI.close()
+        for c in ctxI:
+            c.close()
         ctxD[1].close()
 
     if rank != 0:

@@ -69,14 +69,27 @@ struct DeviceQueue {
 };
 static DeviceQueue g_queue[64];
 
+static double now_ms()
+{
+  static const auto t0 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+static bool trace_calls()
+{
+  static const bool on = getenv("FB200_TRACE") && atoi(getenv("FB200_TRACE")) >= 2;
+  return on;
+}
+
 struct QueueTurn { // one host-buffer call's place in its device's queue; releases what it still holds when it dies
   DeviceQueue *q;
   uint64_t ticket;
   bool copy_done = false, compute_done = false;
+  double t_call = 0, t_copy = 0, t_copy_end = 0, t_compute = 0, t_compute_end = 0; // FB200_TRACE=2: host-side timeline of the call
   explicit QueueTurn(int device) : q(&g_queue[device >= 0 && device < 64 ? device : 0])
   {
     std::lock_guard<std::mutex> lk(q->m);
     ticket = q->next_ticket++;
+    t_call = now_ms();
     if (!q->last_feed) {
       cudaEventCreateWithFlags(&q->last_feed, cudaEventDisableTiming);
       cudaEventCreateWithFlags(&q->last_compute, cudaEventDisableTiming);
@@ -88,11 +101,13 @@ struct QueueTurn { // one host-buffer call's place in its device's queue; releas
     std::unique_lock<std::mutex> lk(q->m);
     q->cv.wait(lk, [&] { return q->copy_turn == ticket; });
     if (q->feed_recorded) cudaStreamWaitEvent(s_in, q->last_feed, 0);
+    t_copy = now_ms();
   }
   void end_copy(cudaStream_t s_in)
   {
     std::lock_guard<std::mutex> lk(q->m);
     if (copy_done) return;
+    t_copy_end = now_ms();
     if (s_in) { cudaEventRecord(q->last_feed, s_in); q->feed_recorded = true; }
     copy_done = true;
     q->copy_turn = ticket + 1;
@@ -103,16 +118,24 @@ struct QueueTurn { // one host-buffer call's place in its device's queue; releas
     std::unique_lock<std::mutex> lk(q->m);
     q->cv.wait(lk, [&] { return q->compute_turn == ticket; });
     if (q->compute_recorded) cudaStreamWaitEvent(st, q->last_compute, 0);
+    t_compute = now_ms();
   }
   // st: the stream on which everything this call launched has been (or has been made to be) ordered
   void end_compute(cudaStream_t st)
   {
     std::lock_guard<std::mutex> lk(q->m);
     if (compute_done) return;
+    t_compute_end = now_ms();
     if (st) { cudaEventRecord(q->last_compute, st); q->compute_recorded = true; }
     compute_done = true;
     q->compute_turn = ticket + 1;
     q->cv.notify_all();
+  }
+  void trace(const char *what, double t_kernels_done) const
+  {
+    if (trace_calls())
+      fprintf(stderr, "[fb200] #%llu %-7s call %.2f | copies queued %.2f..%.2f | kernels queued %.2f..%.2f | kernels done %.2f | return %.2f ms\n",
+              (unsigned long long)ticket, what, t_call, t_copy, t_copy_end, t_compute, t_compute_end, t_kernels_done, now_ms());
   }
   ~QueueTurn()
   {
@@ -170,6 +193,7 @@ struct fb200_ctx {
   // the watermark included, between passes) need the copies to have finished before the launch, which is what
   // overlap_h2d == false selects: no watermark, the kernel is ordered behind the last chunk.
   bool overlap_h2d = true;
+  double t_kernels_done = 0; // FB200_TRACE=2
   // fb200_*_async: the blocking call runs on a helper thread; fb200_wait joins it (one call in flight per context)
   std::thread worker;
   bool async_pending = false;
@@ -556,8 +580,9 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
   ctx->stage_begin(FB200_STAGE_SETUP);
   launch_count_blocks(j, st);
   launch_scan_u64(j.stream_blk0, j.stream_blk0, ns, st);
-  launch_gather_u64(ctx->d_group_bounds.as<uint64_t>(), j.stream_blk0, gs, ns, ngroups + 1, st);
-  CK(cudaMemcpyAsync(h_bb, ctx->d_group_bounds.p, (ngroups + 1) * 8, cudaMemcpyDeviceToHost, st));
+  // (the group bounds go straight into pinned host memory, written by the kernel: a small D2H copy would queue
+  // behind the bulk copies of other calls in the copy engine, and the host waits for these few bytes below)
+  launch_gather_u64(h_bb, j.stream_blk0, gs, ns, ngroups + 1, st);
   CK(cudaEventRecord(ctx->e_bounds, st));
   launches += 3;
   uint64_t nb = io.nb_known, n_multi = io.n_multi, nmb = io.nmb;
@@ -729,6 +754,7 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
     CK(cudaEventRecord(ctx->ev0[FB200_STAGE_PACK], st)); // = end of the parse (stream order)
     CK(cudaStreamSynchronize(ctx->s_post));
     CK(cudaStreamSynchronize(ctx->s_post2));
+    ctx->t_kernels_done = now_ms();
     CK(cudaEventRecord(ctx->ev1[FB200_STAGE_PACK], st));
     ctx->ev_used[FB200_STAGE_PACK] = true;
   }
@@ -914,6 +940,7 @@ static int deflate_host_common(fb200_ctx *ctx, const uint8_t *src, uint64_t n, c
   CK(cudaStreamSynchronize(st));
   CK(cudaStreamSynchronize(ctx->s_in));
   ctx->stats.kernel_launches += 1;
+  turn.trace("deflate", ctx->t_kernels_done);
   return FB200_OK;
 }
 
@@ -1062,7 +1089,6 @@ static int inflate_launch(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t 
   launch_inflate_exact(j, ctx->num_sms, st);
   ctx->stage_end(FB200_STAGE_INFLATE);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(ctx->pinned, j.counters, 32, cudaMemcpyDeviceToHost, st));
   ctx->stats = fb200_stats{};
   ctx->stats.kernel_launches = launches;
   return FB200_OK;
@@ -1070,6 +1096,9 @@ static int inflate_launch(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t 
 
 static int inflate_finish(fb200_ctx *ctx)
 {
+  // (queued here, not behind the kernels in inflate_launch: a host-buffer call records its "kernels done" event for
+  // the next call's kernels right after the launch, and this small copy waits behind bulk D2H copies in the copy engine)
+  CK(cudaMemcpyAsync(ctx->pinned, ctx->counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->stats.inflate_fallbacks = reinterpret_cast<const uint32_t *>(ctx->pinned)[2];
   if (getenv("FB200_TRACE"))
@@ -1220,6 +1249,7 @@ extern "C" int fb200_inflate_batch(fb200_ctx *ctx, const uint8_t *comp, const ui
   CK(cudaStreamSynchronize(ctx->s_in));
   CK(cudaStreamSynchronize(ctx->s_out));
   ctx->stats.kernel_launches += 2;
+  turn.trace("inflate", t_kdone - t0 + turn.t_call);
   if (trace)
     fprintf(stderr, "[fb200] inflate host: groups=%llu fed=%.2f first_flag=%.2f last_flag=%.2f kernels_done=%.2f end=%.2f ms\n",
             (unsigned long long)ngroups, t_fed - t0, t_first - t0, t_last - t0, t_kdone - t0, now() - t0);
