@@ -461,7 +461,7 @@ def main():
             sizes = dc.d_doff[1:] - dc.d_doff[:-1]
             if peer:
                 frame_len[0] = peer.put(dc.d_dst, sizes, seg or 0, nseg_total=units_total)
-                peer.wait()  # every rank's payload and the header are in GPU 0's frame
+                peer.wait()  # this rank's payload and the header are in GPU 0's frame
                 peer.get(first, nunits, d_fcomp, d_fcoff)
                 dc.inflate(d_fcomp, d_fcoff)
             else:
@@ -484,6 +484,8 @@ def main():
     dc.d_out.zero_()
     step(record=False)  # same load right before the timed region (also keeps the clocks up for the sampler)
     torch.cuda.synchronize()
+    if peer:
+        peer.wait_all()
     n_checked = dc.check(h_np, off, oracle)  # inflate(what came out of the frame) == input; sample == oracle
     clen = dc.clen
     if world > 1 and rank == 0:  # the assembled frame: sample streams of every rank inflate to that rank's units

@@ -538,7 +538,8 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
   CK(ctx->stream_bytes.ensure((ns + 1) * 8));
   CK(ctx->stream_trailer.ensure((ns + 1) * 8));
   CK(ctx->counters.ensure(64));
-  CK(ctx->d_group.ensure(fb200_ctx::kMaxGroups * 4));
+  static_assert(kBuildCounterStride == fb200_ctx::kMaxGroups, "one K3 counter pair per group");
+  CK(ctx->d_group.ensure(2 * fb200_ctx::kMaxGroups * 4));
   CK(ctx->d_group_bounds.ensure((fb200_ctx::kMaxGroups + 1) * 8));
   j.stream_blk0 = ctx->stream_blk0.as<uint64_t>();
   j.stream_bytes = ctx->stream_bytes.as<uint64_t>();
@@ -565,7 +566,7 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
   }
   const uint64_t ngroups = ns ? (ns + gs - 1) / gs : 0;
   uint32_t *d_k3cnt = ctx->d_group.as<uint32_t>();
-  CK(cudaMemsetAsync(d_k3cnt, 0, fb200_ctx::kMaxGroups * 4, st));
+  CK(cudaMemsetAsync(d_k3cnt, 0, 2 * fb200_ctx::kMaxGroups * 4, st));
   while (ctx->e_gsize.size() < ngroups) {
     cudaEvent_t e0, e1, e2;
     CK(cudaEventCreate(&e0)); // (timed: FB200_TRACE prints the group timeline)

@@ -90,25 +90,45 @@ void launch_histogram(const DeflateJob &j, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------
-// K3: code construction.  One warp per block, working set in shared memory (huff_build.cuh).
-constexpr int kBuildWarps = 18; // 11.8 KB of scratch per warp
+// K3: code construction.  One warp per block, working set in shared memory (huff_build.cuh).  Two passes: blocks
+// whose literal/length alphabet has at most 128 symbols in use (small blocks, text) are built with the small
+// scratch at 32 warps per SM; the pass marks the others (blk_hdr_nbits = kNeedsBigScratch) for the second pass
+// with the full-size scratch at 18 warps per SM.
+constexpr int kBuildWarpsBig = 18;   // 12.5 KB of scratch per warp
+constexpr int kBuildWarpsSmall = 32; // 6.9 KB
+constexpr int kSmallSyms = 128;
+constexpr uint32_t kNeedsBigScratch = 0xffffffffu;
 
-__global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(DeflateJob j)
+template <int NS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_build_codes(DeflateJob j, uint32_t *work_counter)
 {
   extern __shared__ __align__(16) uint8_t build_smem[];
-  HuffScratch &S = reinterpret_cast<HuffScratch *>(build_smem)[threadIdx.x >> 5];
+  using SC = HuffScratchT<NS>;
+  SC &S = reinterpret_cast<SC *>(build_smem)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
   for (;;) { // blocks differ a lot in cost (alphabet size): hand them out one at a time
     uint32_t b32 = 0;
-    if ((threadIdx.x & 31) == 0) b32 = atomicAdd(j.work_counter, 1u);
+    if (lane == 0) b32 = atomicAdd(work_counter, 1u);
     b32 = __shfl_sync(kFull, b32, 0);
     if (j.blk_begin + b32 >= j.blk_end) break;
     const uint64_t blk = j.blk_begin + b32;
     const int kind = j.blk_kind[blk];
     if (kind == kKindStored) continue;
+    const uint32_t *gfreq = j.blk_freq + blk * kFreqStride;
+    if (NS < kMaxSyms) { // small pass: count the literal/length symbols in use
+      int used = 0;
+      for (int i = lane; i < kNumLit; i += 32) used += gfreq[i] != 0;
+      used = __reduce_add_sync(kFull, used);
+      if (used > NS) {
+        if (lane == 0) j.blk_hdr_nbits[blk] = kNeedsBigScratch;
+        continue;
+      }
+    } else if (j.blk_hdr_nbits[blk] != kNeedsBigScratch) {
+      continue; // built by the small pass
+    }
     const BlockRef r = block_ref(j, blk);
-    const BlockBuild res = build_block_warp(j.blk_freq + blk * kFreqStride, kind, r.n, j.blk_code + blk * kFreqStride,
-                                            j.blk_hdr + blk * kHdrWords, S);
-    if ((threadIdx.x & 31) == 0) {
+    const BlockBuild res = build_block_warp(gfreq, kind, r.n, j.blk_code + blk * kFreqStride, j.blk_hdr + blk * kHdrWords, S);
+    if (lane == 0) {
       j.blk_kind[blk] = (uint8_t)res.kind;
       j.blk_hdr_nbits[blk] = res.hdr_nbits;
       j.blk_bits[blk] = res.blk_bits;
@@ -117,19 +137,23 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(DeflateJob j)
   }
 }
 
-void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st, int warps_per_cta)
+void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st)
 {
   if (j.blk_end <= j.blk_begin) return;
-  int w = warps_per_cta;
-  if (w < 1) w = 1;
-  if (w > kBuildWarps) w = kBuildWarps;
-  const int smem = w * (int)sizeof(HuffScratch);
   // enough CTAs to fill the GPU when the kernel has it to itself (the blocks are handed out dynamically)
   const uint64_t nb = j.blk_end - j.blk_begin;
-  const uint64_t want = (nb + w - 1) / w;
-  const uint64_t full = (uint64_t)num_sms * (uint64_t)(kBuildWarps / w);
-  const unsigned g = (unsigned)(want < full ? want : full);
-  k_build_codes<<<g, w * 32, smem, st>>>(j);
+  {
+    const uint64_t want = (nb + kBuildWarpsSmall - 1) / kBuildWarpsSmall;
+    const unsigned g = (unsigned)(want < (uint64_t)num_sms ? want : (uint64_t)num_sms);
+    k_build_codes<kSmallSyms, kBuildWarpsSmall>
+        <<<g, kBuildWarpsSmall * 32, kBuildWarpsSmall * (int)sizeof(HuffScratchT<kSmallSyms>), st>>>(j, j.work_counter);
+  }
+  {
+    const uint64_t want = (nb + kBuildWarpsBig - 1) / kBuildWarpsBig;
+    const unsigned g = (unsigned)(want < (uint64_t)num_sms ? want : (uint64_t)num_sms);
+    k_build_codes<kMaxSyms, kBuildWarpsBig>
+        <<<g, kBuildWarpsBig * 32, kBuildWarpsBig * (int)sizeof(HuffScratch), st>>>(j, j.work_counter + kBuildCounterStride);
+  }
 }
 
 // ------------------------------------------------------------------
@@ -387,10 +411,14 @@ void launch_zero_range(const DeflateJob &j, cudaStream_t st)
 void preload_encode_kernels()
 {
   // function attributes are per device: set when the context is created
-  cudaFuncSetAttribute(k_build_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildWarps * (int)sizeof(HuffScratch));
+  cudaFuncSetAttribute(k_build_codes<kSmallSyms, kBuildWarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       kBuildWarpsSmall * (int)sizeof(HuffScratchT<kSmallSyms>));
+  cudaFuncSetAttribute(k_build_codes<kMaxSyms, kBuildWarpsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       kBuildWarpsBig * (int)sizeof(HuffScratch));
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_histogram);
-  cudaFuncGetAttributes(&a, k_build_codes);
+  cudaFuncGetAttributes(&a, k_build_codes<kSmallSyms, kBuildWarpsSmall>);
+  cudaFuncGetAttributes(&a, k_build_codes<kMaxSyms, kBuildWarpsBig>);
   cudaFuncGetAttributes(&a, k_zero_range);
   cudaFuncGetAttributes(&a, k_layout);
   cudaFuncGetAttributes(&a, k_pack);

@@ -83,17 +83,19 @@ FB_HD inline int wmax(int v)
 }
 
 constexpr int kMaxSyms = 288;
-constexpr int kSortPad = 512;
-constexpr int kMaskWords = 2 * kMaxSyms / 32; // one bit per list position
 
-// Per-warp working set (shared memory on the device).
-struct HuffScratch {
-  uint32_t keys[kSortPad];          // (freq << 9) | literal, ascending == by_frequency (huffman-code.mbt:346-351)
-  uint32_t lista[2 * kMaxSyms];     // package-merge lists (weights), double buffered
-  uint32_t listb[2 * kMaxSyms];
-  uint32_t pairs[kMaxSyms];
-  uint32_t leafmask[16][kMaskWords]; // bit p set: item p of list_k is a leaf (1.1 KB instead of 9 KB of leaf positions:
-                                    // the warp's scratch is what caps the kernel's occupancy)
+// Per-warp working set (shared memory on the device), for alphabets with at most NS symbols IN USE.  The warp's
+// scratch is what caps the kernel's occupancy: blocks whose literal/length alphabet has <= 128 used symbols
+// (small blocks, text) are built with the 6.9 KB variant, 32 warps per SM instead of 18.
+template <int NS>
+struct HuffScratchT {
+  static constexpr int kSyms = NS;
+  static constexpr int kPad = NS <= 32 ? 32 : NS <= 64 ? 64 : NS <= 128 ? 128 : NS <= 256 ? 256 : 512; // bitonic sort width
+  static constexpr int kMaskWords = 2 * NS / 32;                                                      // one bit per list position
+  uint32_t keys[kPad];              // (freq << 9) | literal, ascending == by_frequency (huffman-code.mbt:346-351)
+  uint32_t lists[4 * NS];           // package-merge lists (weights), double buffered; later: run table, header staging
+  uint32_t pairs[NS];
+  uint32_t leafmask[16][kMaskWords]; // bit p set: item p of list_k is a leaf
   uint32_t run[16];                 // canonical code counters
   // block assembly
   uint32_t freq[320];               // lit/len (286) ++ offset (30) histogram
@@ -103,14 +105,17 @@ struct HuffScratch {
   uint8_t cglen[32];
   uint16_t cgcode[32];
   uint8_t cg[kNumLit + kNumDist + 4];
+  uint16_t items[kNumLit + kNumDist + 4]; // code-length symbols of the header: symbol | extra << 8
   int misc[8];
 };
+using HuffScratch = HuffScratchT<kMaxSyms>;
+static_assert(4 * 128 * 4 >= 2 * 320 * 2 && 4 * 128 * 4 >= kHdrWords * 4, "lists[] also hosts the run table and the header staging");
 
 #if defined(__CUDA_ARCH__)
 // One package-merge level on the device: each lane owns up to Q leaves and Q pairs; their (branch-free)
 // binary searches advance in lockstep so the shared-memory loads are independent.
-template <int Q, int TOP>
-__device__ __forceinline__ void pm_merge_level(HuffScratch &S, int k, int n, int np, int cap, uint32_t *cur)
+template <int Q, int TOP, class SC>
+__device__ __forceinline__ void pm_merge_level(SC &S, int k, int n, int np, int cap, uint32_t *cur)
 {
   int lo[Q];
   uint32_t w[Q];
@@ -163,9 +168,10 @@ __device__ __forceinline__ void pm_merge_level(HuffScratch &S, int k, int n, int
 #endif
 
 // HuffmanEncoder::generate (:295-343): freq[0..nsym) -> len[] (0 for unused symbols), code[] bit-reversed.
-FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, uint8_t *len, uint16_t *code,
-                                HuffScratch &S)
+template <class SC>
+FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, uint8_t *len, uint16_t *code, SC &S)
 {
+  constexpr int kMaskWords = SC::kMaskWords;
   // gather the used symbols (any order: the sort below orders them), pad to a power of two
   int first = nsym, n = 0;
 #if defined(__CUDA_ARCH__)
@@ -204,7 +210,7 @@ FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, ui
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
 #if defined(__CUDA_ARCH__)
-      if (P >= 256) { // several independent compare-exchanges per lane and stage
+      if (SC::kPad >= 256 && P >= 256) { // several independent compare-exchanges per lane and stage
         uint32_t a[8], b[8];
         int ia[8];
         const int nq = P >> 6;
@@ -234,7 +240,7 @@ FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, ui
   // package-merge lists (bit_counts :112-244)
   const int mb = max_bits < n - 1 ? max_bits : n - 1; // :126-129
   const int cap = 2 * n - 2;
-  uint32_t *prev = S.lista, *cur = S.listb;
+  uint32_t *prev = S.lists, *cur = S.lists + 2 * SC::kSyms;
   FB_PFOR(i, 16 * kMaskWords) (&S.leafmask[0][0])[i] = 0;
   FB_PFOR(i, n) prev[i] = S.keys[i] >> 9;
   int plen = n;
@@ -246,7 +252,7 @@ FB_HD inline void warp_generate(const uint32_t *freq, int nsym, int max_bits, ui
 #if defined(__CUDA_ARCH__)
     if (n <= 32) pm_merge_level<1, 32>(S, k, n, np, cap, cur);
     else if (n <= 64) pm_merge_level<2, 64>(S, k, n, np, cap, cur);
-    else if (n <= 128) pm_merge_level<4, 128>(S, k, n, np, cap, cur);
+    else if (SC::kSyms <= 128 || n <= 128) pm_merge_level<4, 128>(S, k, n, np, cap, cur);
     else pm_merge_level<9, 256>(S, k, n, np, cap, cur);
 #else
     FB_PFOR(i, n) { // leaf i sits after every pair of weight <= its own
@@ -380,6 +386,37 @@ struct BitAcc {
   }
 };
 
+// symbols a run of `count` equal code lengths `size` emits (generate_codegen, hbw:241-330)
+FB_HD inline int codegen_run_items(int size, int count)
+{
+  if (size != 0) {
+    const int c = count - 1;
+    return 1 + c / 6 + (c % 6 >= 3 ? 1 : c % 6);
+  }
+  const int r = count % 138;
+  return count / 138 + (r >= 3 ? 1 : r);
+}
+
+// bits of one codegen item (symbol | extra << 8): the symbol's code, then 2 / 3 / 7 extra bits behind 16 / 17 / 18
+FB_HD inline void codegen_item_bits(uint16_t item, const uint16_t *cgcode, const uint8_t *cglen, uint32_t &v, int &nb)
+{
+  const int sym = item & 0xff, extra = item >> 8;
+  v = cgcode[sym];
+  nb = cglen[sym];
+  const int xb = sym == 16 ? 2 : (sym == 17 ? 3 : (sym == 18 ? 7 : 0));
+  v |= (uint32_t)extra << nb;
+  nb += xb;
+}
+
+FB_HD inline void fb_add(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+
 // Everything write_block_dynamic / write_block_huff decide before the first
 // payload bit (hbw:496-534, :738-787): codes, codegen, "store instead" test,
 // header bit string, exact block size.  gfreq = lit/len[286] ++ offset[30]
@@ -390,8 +427,9 @@ struct BlockBuild {
   uint32_t blk_bits;  // header + payload + EOB
 };
 
+template <class SC>
 FB_HD inline BlockBuild build_block_warp(const uint32_t *gfreq, int kind, uint32_t n, uint32_t *codeout,
-                                         uint32_t *hdr_words, HuffScratch &S)
+                                         uint32_t *hdr_words, SC &S)
 {
   BlockBuild res;
   res.kind = kind;
@@ -428,41 +466,90 @@ FB_HD inline BlockBuild build_block_warp(const uint32_t *gfreq, int kind, uint32
     FB_WSYNC();
   }
 
-  // generate_codegen (hbw:241-330): serial RLE over <= 316 lengths
+  // generate_codegen (hbw:241-330).  The reference walks the <= 316 code lengths once and emits, run by run,
+  // the code-length symbols 0..15 / 16 (repeat previous 3..6 times) / 17 (3..10 zeros) / 18 (11..138 zeros) with
+  // their extra values.  What a run of `count` equal lengths `size` emits depends on (size, count) alone:
+  //   size != 0: size, then c = count - 1 copies as  c / 6 x (16, extra 3), one (16, extra c % 6 - 3) if c % 6 >= 3,
+  //              and the remaining c % 6 < 3 copies written out;
+  //   size == 0: count / 138 x (18, extra 127), one (18, extra r - 11) if r = count % 138 >= 11, else one
+  //              (17, extra r - 3) if r >= 3, else r zeros written out.
+  // So the runs are found in parallel, every run computes how many symbols it emits, a prefix sum places them,
+  // and every run writes its own.  The symbols are kept as items (symbol | extra << 8) in S.items; the header
+  // emission below places their bits with a second prefix sum.
   FB_PFOR(i, 32) S.cgfreq[i] = 0;
   FB_PFOR(i, num_literals) S.cg[i] = S.len[i];
   FB_PFOR(i, num_offsets) S.cg[num_literals + i] = S.len[kNumLit + i];
   FB_WSYNC();
-  if (FB_LANE == 0) {
-    uint8_t *cg = S.cg;
-    uint32_t *cgfreq = S.cgfreq;
-    cg[num_literals + num_offsets] = 255;
-    uint8_t size = cg[0];
-    int count = 1, out = 0;
-    for (int in = 1; size != 255; in++) {
-      const uint8_t next = cg[in];
-      if (next == size) { count++; continue; }
-      if (size != 0) {
-        cg[out++] = size; cgfreq[size]++; count--;
-        while (count >= 3) {
-          const int nn = count < 6 ? count : 6;
-          cg[out++] = 16; cg[out++] = (uint8_t)(nn - 3); cgfreq[16]++; count -= nn;
-        }
-      } else {
-        while (count >= 11) {
-          const int nn = count < 138 ? count : 138;
-          cg[out++] = 18; cg[out++] = (uint8_t)(nn - 11); cgfreq[18]++; count -= nn;
-        }
-        if (count >= 3) {
-          cg[out++] = 17; cg[out++] = (uint8_t)(count - 3); cgfreq[17]++; count = 0;
-        }
-      }
-      count--;
-      for (; count >= 0; count--) { cg[out++] = size; cgfreq[size]++; }
-      size = next;
-      count = 1;
+  const int ncl = num_literals + num_offsets;
+  uint16_t *rstart = reinterpret_cast<uint16_t *>(S.lists);       // [<= 317] first position of every run (+ end)
+  uint16_t *roff = reinterpret_cast<uint16_t *>(S.lists) + 320;   // [<= 317] first item of every run
+  int nruns = 0;
+#if defined(__CUDA_ARCH__)
+  {
+    const int lane = FB_LANE;
+    const unsigned ltm = (1u << lane) - 1u;
+    for (int base = 0; base < ncl; base += 32) {
+      const int i = base + lane;
+      const bool st = i < ncl && (i == 0 || S.cg[i] != S.cg[i - 1]);
+      const unsigned m = __ballot_sync(0xffffffffu, st);
+      if (st) rstart[nruns + __popc(m & ltm)] = (uint16_t)i;
+      nruns += __popc(m);
     }
-    cg[out] = 255;
+  }
+#else
+  for (int i = 0; i < ncl; i++)
+    if (i == 0 || S.cg[i] != S.cg[i - 1]) rstart[nruns++] = (uint16_t)i;
+#endif
+  if (FB_LANE == 0) rstart[nruns] = (uint16_t)ncl;
+  FB_WSYNC();
+  // symbols every run emits -> exclusive prefix sum
+  int nitems = 0;
+#if defined(__CUDA_ARCH__)
+  for (int base = 0; base < nruns; base += 32) {
+    const int r = base + FB_LANE;
+    int e = 0;
+    if (r < nruns) e = codegen_run_items(S.cg[rstart[r]], (int)rstart[r + 1] - (int)rstart[r]);
+    int x = e;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (FB_LANE >= o) x += y;
+    }
+    if (r < nruns) roff[r] = (uint16_t)(nitems + x - e);
+    nitems += __shfl_sync(0xffffffffu, x, 31);
+  }
+#else
+  for (int r = 0; r < nruns; r++) {
+    roff[r] = (uint16_t)nitems;
+    nitems += codegen_run_items(S.cg[rstart[r]], (int)rstart[r + 1] - (int)rstart[r]);
+  }
+#endif
+  FB_WSYNC();
+  FB_PFOR(r, nruns) {
+    const int size = S.cg[rstart[r]];
+    int count = (int)rstart[r + 1] - (int)rstart[r];
+    uint16_t *it = S.items + roff[r];
+    int o = 0;
+    if (size != 0) {
+      it[o++] = (uint16_t)size;
+      int c = count - 1;
+      const int full = c / 6, r6 = c % 6;
+      for (int q = 0; q < full; q++) it[o++] = (uint16_t)(16 | (3 << 8));
+      int rem = r6;
+      if (r6 >= 3) { it[o++] = (uint16_t)(16 | ((r6 - 3) << 8)); rem = 0; }
+      for (int q = 0; q < rem; q++) it[o++] = (uint16_t)size;
+      fb_add(&S.cgfreq[size], (uint32_t)(1 + rem));
+      if (full + (r6 >= 3)) fb_add(&S.cgfreq[16], (uint32_t)(full + (r6 >= 3)));
+    } else {
+      const int full = count / 138, r138 = count % 138;
+      for (int q = 0; q < full; q++) it[o++] = (uint16_t)(18 | (127 << 8));
+      int rem = r138;
+      if (r138 >= 11) { it[o++] = (uint16_t)(18 | ((r138 - 11) << 8)); rem = 0; }
+      else if (r138 >= 3) { it[o++] = (uint16_t)(17 | ((r138 - 3) << 8)); rem = 0; }
+      for (int q = 0; q < rem; q++) it[o++] = 0;
+      if (full + (r138 >= 11)) fb_add(&S.cgfreq[18], (uint32_t)(full + (r138 >= 11)));
+      if (r138 >= 3 && r138 < 11) fb_add(&S.cgfreq[17], 1u);
+      if (rem) fb_add(&S.cgfreq[0], (uint32_t)rem);
+    }
   }
   FB_WSYNC();
   warp_generate(S.cgfreq, kNumCodegen, 7, S.cglen, S.cgcode, S);
@@ -499,26 +586,59 @@ FB_HD inline BlockBuild build_block_warp(const uint32_t *gfreq, int kind, uint32
     return res;
   }
 
-  // write_dynamic_header (hbw:421-471): serial bit append
+  // write_dynamic_header (hbw:421-471): 3 + 5 + 5 + 4 bits, the code-length code's lengths in codegen order, then
+  // the items (code, then 2 / 3 / 7 extra bits behind symbols 16 / 17 / 18).  Bit positions by prefix sum, bits
+  // ORed into a staging copy of the header words.
+  uint32_t *stage = S.lists; // [kHdrWords] (the package-merge lists are free by now)
+  FB_PFOR(i, kHdrWords) stage[i] = 0;
+  FB_WSYNC();
+  const int fixed_bits = 17 + 3 * num_codegens;
   if (FB_LANE == 0) {
     BitAcc ba;
-    ba.words = hdr_words;
+    ba.words = stage;
     ba.acc = 0; ba.nacc = 0; ba.nwords = 0;
     ba.put(4, 3); // BFINAL = 0, BTYPE = 10
     ba.put((uint32_t)(num_literals - 257), 5);
     ba.put((uint32_t)(num_offsets - 1), 5);
     ba.put((uint32_t)(num_codegens - 4), 4);
     for (int i = 0; i < num_codegens; i++) ba.put(S.cglen[order[i]], 3);
-    for (int i = 0;;) {
-      const int cw = S.cg[i++];
-      if (cw == 255) break;
-      ba.put(S.cgcode[cw], S.cglen[cw]);
-      if (cw == 16) ba.put(S.cg[i++], 2);
-      else if (cw == 17) ba.put(S.cg[i++], 3);
-      else if (cw == 18) ba.put(S.cg[i++], 7);
-    }
-    S.misc[0] = ba.finish();
+    ba.finish();
   }
+  FB_WSYNC();
+  int bitpos = fixed_bits;
+#if defined(__CUDA_ARCH__)
+  for (int base = 0; base < nitems; base += 32) {
+    const int k = base + FB_LANE;
+    uint32_t v = 0;
+    int nb = 0;
+    if (k < nitems) codegen_item_bits(S.items[k], S.cgcode, S.cglen, v, nb);
+    int x = nb;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (FB_LANE >= o) x += y;
+    }
+    if (nb) {
+      const int at = bitpos + x - nb;
+      const uint64_t sh = (uint64_t)v << (at & 31);
+      atomicOr(&stage[at >> 5], (uint32_t)sh);
+      if ((uint32_t)(sh >> 32)) atomicOr(&stage[(at >> 5) + 1], (uint32_t)(sh >> 32));
+    }
+    bitpos += __shfl_sync(0xffffffffu, x, 31);
+  }
+#else
+  for (int k = 0; k < nitems; k++) {
+    uint32_t v = 0;
+    int nb = 0;
+    codegen_item_bits(S.items[k], S.cgcode, S.cglen, v, nb);
+    const uint64_t sh = (uint64_t)v << (bitpos & 31);
+    stage[bitpos >> 5] |= (uint32_t)sh;
+    stage[(bitpos >> 5) + 1] |= (uint32_t)(sh >> 32);
+    bitpos += nb;
+  }
+#endif
+  FB_WSYNC();
+  FB_PFOR(i, (bitpos + 31) >> 5) hdr_words[i] = stage[i];
+  if (FB_LANE == 0) S.misc[0] = bitpos;
   FB_WSYNC();
   const int hdr_bits = S.misc[0];
   res.hdr_nbits = (uint32_t)hdr_bits;

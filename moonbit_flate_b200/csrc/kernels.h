@@ -85,7 +85,9 @@ void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *c
 void launch_histogram(const DeflateJob &j, cudaStream_t st);
 // K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,
 //     huffman-bit-writer.mbt:241-471)
-void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st, int warps_per_cta = 18);
+// j.work_counter: two zeroed uint32 per launch, kBuildCounterStride apart (small-scratch pass, full-size pass)
+constexpr int kBuildCounterStride = 256;
+void launch_build_codes(const DeflateJob &j, int num_sms, cudaStream_t st);
 // layout: per-stream bit offsets, stream sizes, output offsets
 void launch_layout(const DeflateJob &j, cudaStream_t st);
 // K4: bit packing (huffman-bit-writer.mbt:596-824, :474-487) + stream trailers

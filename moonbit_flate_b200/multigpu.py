@@ -197,6 +197,7 @@ class PeerFrame:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         self.available = bool(int(flag.item()))
         self._holder = None
+        self._hdr_flag = None
         self.length = 0
         self.view: Optional[torch.Tensor] = None
         if not self.available:
@@ -228,6 +229,18 @@ class PeerFrame:
                                d_comp_off.data_ptr())
 
     def wait(self):
+        """This rank's payload has landed in the frame and the header (written by rank 0) is complete: everything
+        this rank reads back with ``get`` is there.  No barrier: a rank does not wait for the payloads of the others,
+        so while late ranks still put (into GPU 0) early ranks already get (out of GPU 0) -- NVLink is full duplex."""
+        self.ctx.mg_wait()
+        if self.world > 1:
+            if self._hdr_flag is None:
+                self._hdr_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            dist.broadcast(self._hdr_flag, src=0)  # ordered behind rank 0's header write on its stream
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def wait_all(self):
+        """Every rank's payload is in the frame (the assembled frame is complete)."""
         self.ctx.mg_wait()
         if self.world > 1:
             dist.barrier()
