@@ -175,9 +175,17 @@ int fb200_mg_get(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint
 /* Streaming objects mirroring the reference API (host buffers).       */
 typedef struct fb200_writer fb200_writer;
 /* sink is called with each run of compressed bytes (the &@io.Writer passed to
- * Writer::new, writer.mbt:10); return 0 on success, non-zero = sticky I/O error. */
+ * Writer::new, writer.mbt:10); return 0 on success, non-zero = sticky I/O error.
+ * Like Compressor::write (deflate.mbt:280-294), a write compresses every 65535-byte
+ * window it has completed and hands the bytes to the sink before it returns: at most
+ * one window stays buffered, whatever the length of the stream.  sink == NULL selects
+ * the pull form for hosts that cannot pass a callback: the bytes queue up inside the
+ * object and are collected with fb200_writer_take after each write / close. */
 typedef int (*fb200_sink_fn)(void *user, const uint8_t *data, uint64_t n);
 fb200_writer *fb200_writer_new(fb200_ctx *ctx, fb200_sink_fn sink, void *user);
+/* pull form: compressed bytes waiting / moves up to cap of them to dst, returns the count */
+uint64_t fb200_writer_pending(const fb200_writer *w);
+uint64_t fb200_writer_take(fb200_writer *w, uint8_t *dst, uint64_t cap);
 /* Writer::new_dict (writer.mbt:25-31): the dictionary is compressed into the
  * output as if it had been written first (reference quirk, deflate_test.mbt:12-35). */
 fb200_writer *fb200_writer_new_dict(fb200_ctx *ctx, fb200_sink_fn sink, void *user, const uint8_t *dict,
@@ -203,6 +211,10 @@ int fb200_reader_reset(fb200_reader *r, const uint8_t *comp, uint64_t n, const u
  * count; *status = -1 while the reference returns (n, None), otherwise the
  * FB200_ST_* code delivered together with the last bytes. */
 uint64_t fb200_reader_read(fb200_reader *r, uint8_t *buf, uint64_t n, int32_t *status, int64_t *err_off);
+/* Input bytes the decoder consumed (the reference pulls its input byte by byte and stops right behind the final
+ * block, inflate.mbt:789-799): whatever follows comp[consumed] -- a gzip / zlib trailer, the next member --
+ * belongs to the caller.  Decodes the stream if no read has done so yet. */
+uint64_t fb200_reader_consumed(fb200_reader *r);
 /* impl @io.Closer for Decompressor (inflate.mbt:410-415): FB200_ST_EOF* -> 0. */
 int fb200_reader_close(fb200_reader *r);
 void fb200_reader_free(fb200_reader *r);

@@ -93,6 +93,8 @@ ABI = {
     "fb200_writer_new_dict": (C.c_void_p, [C.c_void_p, SINK_FN, C.c_void_p, _u8p, C.c_uint64]),
     "fb200_writer_write": (C.c_int64, [C.c_void_p, _u8p, C.c_uint64]),
     "fb200_writer_close": (C.c_int, [C.c_void_p]),
+    "fb200_writer_pending": (C.c_uint64, [C.c_void_p]),
+    "fb200_writer_take": (C.c_uint64, [C.c_void_p, _u8p, C.c_uint64]),
     "fb200_writer_free": (None, [C.c_void_p]),
     "fb200_inflate_dict": (C.c_int, [C.c_void_p, _u8p, C.c_uint64, _u8p, C.c_uint64, _u8p, C.c_uint64, _u64p, C.c_void_p,
                                      C.c_void_p, _u64p]),
@@ -100,6 +102,7 @@ ABI = {
     "fb200_reader_new_dict": (C.c_void_p, [C.c_void_p, _u8p, C.c_uint64, _u8p, C.c_uint64]),
     "fb200_reader_reset": (C.c_int, [C.c_void_p, _u8p, C.c_uint64, _u8p, C.c_uint64]),
     "fb200_reader_read": (C.c_uint64, [C.c_void_p, _u8p, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "fb200_reader_consumed": (C.c_uint64, [C.c_void_p]),
     "fb200_reader_close": (C.c_int, [C.c_void_p]),
     "fb200_reader_free": (None, [C.c_void_p]),
     "fb200_last_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
@@ -450,6 +453,10 @@ class Reader:
         eo = C.c_int64(0)
         k = _lib.fb200_reader_read(self._h, _ptr(buf), n, C.byref(st), C.byref(eo))
         return buf[: int(k)].tobytes(), _status_to_err(st.value, eo.value)
+
+    def consumed(self) -> int:
+        """Input bytes the decoder consumed: what follows them (a trailer, the next member) belongs to the caller."""
+        return int(_lib.fb200_reader_consumed(self._h))
 
     def read_all(self):
         """@io.copy(got, r): returns (bytes, err) with err None for a clean ioeof."""

@@ -518,6 +518,11 @@ struct DeflateIo {
   uint8_t *h_dst = nullptr;            // host-buffer calls: where finished groups are copied to
   uint64_t h_cap = 0;
   QueueTurn *turn = nullptr;           // host-buffer calls: place in the device's FIFO (kernel phase)
+  // continuation of one stream across calls (DeflateJob::cont_*): the streaming Writer
+  bool cont_prev = false, cont_open = false;
+  uint32_t cont_start_bit = 0;
+  uint64_t cont_block_base = 0;
+  uint16_t *d_seed = nullptr;          // device [1 << 14]: end table of the previous call (in), of this call (out, cont_open)
 };
 
 static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
@@ -549,6 +554,11 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
   j.avail = io.avail;
   j.dst = io.d_dst;
   j.dst_cap = io.d_cap & ~3ull; // K4 clears and writes whole words
+  j.cont_prev = io.cont_prev ? 1u : 0u;
+  j.cont_open = io.cont_open ? 1u : 0u;
+  j.cont_start_bit = io.cont_start_bit;
+  j.cont_block_base = io.cont_block_base;
+  if ((io.cont_prev || io.cont_open) && (ns != 1 || !io.d_seed)) { ctx->err = "a continued stream is a single stream"; return FB200_ERR_ARG; }
   CK(cudaMemsetAsync(j.counters, 0, 64, st));
   uint64_t launches = 0;
   for (int i = 0; i < FB200_NUM_STAGES; i++) ctx->ev_used[i] = false;
@@ -632,7 +642,7 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
   launch_parse_single(j, ctx->num_sms, ctx->parse_gtables.p, st);
   launches += 1;
   CK(cudaGetLastError());
-  const bool blockpar = n_multi > 0 && (ctx->blockpar == 2 || (ctx->blockpar == 1 && n_multi < 4096));
+  const bool blockpar = n_multi > 0 && (ctx->blockpar == 2 || (ctx->blockpar == 1 && n_multi < 4096) || io.cont_prev || io.cont_open);
   if (n_multi > 0 && !blockpar) {
     launch_parse_multi(j, ctx->num_sms, ctx->parse_gtables.p, st); // one warp per stream, its blocks in sequence
     launches += 1;
@@ -655,6 +665,11 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
     bp.mb_idx = ctx->bp_idx.as<uint64_t>();
     bp.tabs = ctx->bp_tabs.as<uint16_t>();
     bp.nmb = nmb;
+    bp.cont_prev = j.cont_prev;
+    bp.cont_open = j.cont_open;
+    bp.cont_block_base = j.cont_block_base;
+    if (io.cont_prev) // the stand-in block's end table = what the previous call left (copy 0 is every block's latest at first)
+      CK(cudaMemcpyAsync(bp.tabs, io.d_seed, (size_t)kTableSize * 2, cudaMemcpyDeviceToDevice, st));
     uint32_t *h_nlist = reinterpret_cast<uint32_t *>(ctx->pinned + 18);
     uint64_t rounds = 0, parsed_blocks = 0;
     for (int round = 1;; round++) {
@@ -675,6 +690,8 @@ static int deflate_run(fb200_ctx *ctx, const DeflateIo &io, uint64_t *total_out)
       parsed_blocks += bp.nlist;
       if ((uint64_t)round > nmb + 2) { ctx->err = "internal error: block-parallel parse does not converge"; return FB200_ERR_CUDA; }
     }
+    if (io.cont_open) // the end table of the last block, for the next call (bp.lat_next: the round that found nothing to do)
+      launch_bp_save_table(bp, nmb - 1, bp.lat_next, io.d_seed, st);
     CK(cudaGetLastError());
     if (getenv("FB200_TRACE"))
       fprintf(stderr, "[fb200] block-parallel parse: %llu streams, %llu blocks, %llu rounds, %llu block parses\n",
@@ -1308,22 +1325,43 @@ extern "C" int fb200_wait(fb200_ctx *ctx)
 
 // ------------------------------------------------------------------
 // Streaming Writer (writer.mbt:10-58 / deflate.mbt:157-183, :280-294).
-// The compressed bytes are a pure function of the concatenated input (blocks
-// are cut only when the 65535-byte window fills or at close), so the object
-// buffers writes and runs the GPU path at close.
+// Compressor::write copies its input into a 65535-byte window and encodes the window the moment it is full
+// (fill_store / enc_speed, deflate.mbt:222-294); only the last, partial window waits for close.  The object does
+// the same at the granularity of a write call: every write compresses the full windows it has completed and hands
+// their bytes to the sink before it returns, so at most one window (+ the bits of an unfinished byte) stays
+// buffered, whatever the length of the stream.  What carries over from call to call is what the reference's
+// encoder carries over from block to block: the hash table (as the normalised end table of the block-parallel
+// parse, on the device), the last 32768 bytes (a candidate in the previous block is verified on 4 bytes, D1), the
+// number of blocks so far (table resets, deflate-fast.mbt:129-132) and the bit position inside the last byte.
 
 struct fb200_writer {
   fb200_ctx *ctx;
   fb200_sink_fn sink;
   void *user;
-  std::vector<uint8_t> buf;
+  std::vector<uint8_t> pend;  // bytes written and not yet compressed (< 65535 between calls)
+  std::vector<uint8_t> hist;  // the last <= 32768 bytes already compressed
+  std::vector<uint8_t> stage, out;
+  std::vector<uint8_t> outq;  // sink == NULL: compressed bytes waiting for fb200_writer_take
+  bool streaming = false;     // some windows have been compressed: the device holds the continuation state
+  uint64_t blocks_done = 0;
+  uint32_t carry_bits = 0;    // bits of `carry` that belong to the stream so far
+  uint8_t carry = 0;
+  uint16_t *d_seed = nullptr; // device: end table of the last compressed block
   bool closed = false;
   int sticky = 0;
 };
 
+static int writer_deliver(fb200_writer *w, const uint8_t *p, uint64_t n)
+{
+  if (!n) return 0;
+  if (w->sink) return w->sink(w->user, p, n);
+  w->outq.insert(w->outq.end(), p, p + n);
+  return 0;
+}
+
 extern "C" fb200_writer *fb200_writer_new(fb200_ctx *ctx, fb200_sink_fn sink, void *user)
 {
-  if (!ctx || !sink) return nullptr;
+  if (!ctx) return nullptr;
   fb200_writer *w = new (std::nothrow) fb200_writer();
   if (!w) return nullptr;
   w->ctx = ctx;
@@ -1342,8 +1380,79 @@ extern "C" fb200_writer *fb200_writer_new_dict(fb200_ctx *ctx, fb200_sink_fn sin
     dict += n - kMaxMatchOffset;
     n = kMaxMatchOffset;
   }
-  w->buf.assign(dict, dict + n);
+  w->pend.assign(dict, dict + n);
   return w;
+}
+
+// Compresses data[0..n) as the continuation of the writer's stream: n is a multiple of 65535 unless `final`, which
+// also writes the final empty stored block (Compressor::close, deflate.mbt:157-183).
+static int writer_emit(fb200_writer *w, const uint8_t *data, uint64_t n, bool final)
+{
+  fb200_ctx *ctx = w->ctx;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (!w->d_seed) {
+    CK(cudaMalloc((void **)&w->d_seed, (size_t)kTableSize * 2));
+    CK(cudaMemsetAsync(w->d_seed, 0, (size_t)kTableSize * 2, st)); // nothing in reach
+  }
+  // [stand-in block: 65535 bytes, the history at its end][data]
+  const uint64_t total = (uint64_t)kBlockSize + n;
+  w->stage.resize(total);
+  memset(w->stage.data(), 0, (size_t)kBlockSize - w->hist.size());
+  if (!w->hist.empty()) memcpy(w->stage.data() + kBlockSize - w->hist.size(), w->hist.data(), w->hist.size());
+  if (n) memcpy(w->stage.data() + kBlockSize, data, n);
+  const uint64_t dcap = ((fb200_deflate_stream_bound(n) + 64 + 3) & ~3ull);
+  CK(ctx->p_in[1].ensure(total + 256));
+  CK(ctx->p_out[1].ensure(dcap + 16));
+  CK(ctx->p_off_in[1].ensure(64));
+  CK(ctx->p_off_out[1].ensure(64));
+  uint64_t *h = ctx->pinned + 56;
+  h[0] = 0;
+  h[1] = total;
+  CK(cudaMemcpyAsync(ctx->p_in[1].p, w->stage.data(), total, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->p_off_in[1].p, h, 16, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st)); // (the staging vector is pageable)
+  DeflateIo io;
+  io.d_src = ctx->p_in[1].as<uint8_t>();
+  io.d_src_off = ctx->p_off_in[1].as<uint64_t>();
+  io.ns = 1;
+  io.n_total = total;
+  io.d_dst_off = ctx->p_off_out[1].as<uint64_t>();
+  io.d_dst = ctx->p_out[1].as<uint8_t>();
+  io.d_cap = dcap;
+  io.cont_prev = true;
+  io.cont_open = !final;
+  io.cont_start_bit = w->carry_bits;
+  io.cont_block_base = w->blocks_done;
+  io.d_seed = w->d_seed;
+  uint64_t olen = 0;
+  const int rc = deflate_run(ctx, io, &olen);
+  if (rc != FB200_OK) return rc;
+  uint64_t bits_end = olen * 8;
+  if (!final) { // where the last block ended inside the last byte
+    CK(cudaMemcpyAsync(h + 2, ctx->last.stream_trailer_bit, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    bits_end = h[2];
+  }
+  w->out.resize(olen + 1);
+  if (olen) CK(cudaMemcpy(w->out.data(), ctx->p_out[1].p, olen, cudaMemcpyDeviceToHost));
+  if (w->carry_bits && olen) w->out[0] |= w->carry; // the bits the previous call left in this byte
+  uint64_t emit = olen;
+  if (!final) {
+    w->carry_bits = (uint32_t)(bits_end & 7);
+    if (w->carry_bits) { emit = olen - 1; w->carry = w->out[olen - 1]; }
+    else w->carry = 0;
+    w->blocks_done += n / kBlockSize;
+    // history for the next call: the last 32768 bytes of everything compressed so far
+    if (n >= (uint64_t)kMaxMatchOffset) w->hist.assign(data + n - kMaxMatchOffset, data + n);
+    else {
+      w->hist.insert(w->hist.end(), data, data + n);
+      if (w->hist.size() > (size_t)kMaxMatchOffset) w->hist.erase(w->hist.begin(), w->hist.end() - kMaxMatchOffset);
+    }
+    w->streaming = true;
+  }
+  if (writer_deliver(w, w->out.data(), emit) != 0) return FB200_ERR_ARG;
+  return FB200_OK;
 }
 
 extern "C" int64_t fb200_writer_write(fb200_writer *w, const uint8_t *data, uint64_t n)
@@ -1351,7 +1460,13 @@ extern "C" int64_t fb200_writer_write(fb200_writer *w, const uint8_t *data, uint
   if (!w) return FB200_ERR_ARG;
   if (w->closed) return FB200_ERR_CLOSED; // writer_closed_error (deflate.mbt:154, :281-283)
   if (w->sticky) return w->sticky;
-  if (n) w->buf.insert(w->buf.end(), data, data + n);
+  if (n) w->pend.insert(w->pend.end(), data, data + n);
+  const uint64_t full = w->pend.size() / kBlockSize * kBlockSize; // windows that are full now (deflate.mbt:284-291)
+  if (full) {
+    const int rc = writer_emit(w, w->pend.data(), full, false);
+    if (rc != FB200_OK) { w->sticky = rc; return rc; }
+    w->pend.erase(w->pend.begin(), w->pend.begin() + (ptrdiff_t)full);
+  }
   return (int64_t)n;
 }
 
@@ -1360,18 +1475,46 @@ extern "C" int fb200_writer_close(fb200_writer *w)
   if (!w) return FB200_ERR_ARG;
   if (w->closed) return FB200_OK; // deflate.mbt:158-160
   if (w->sticky) return w->sticky;
-  const uint64_t n = w->buf.size();
-  std::vector<uint8_t> out(fb200_deflate_stream_bound(n));
-  uint64_t off[2] = {0, n}, doff[2], olen = 0;
-  int rc = fb200_deflate_streams(w->ctx, w->buf.data(), off, 1, out.data(), out.size(), doff, &olen);
+  int rc;
+  if (!w->streaming) { // nothing compressed yet: the whole stream in one call
+    const uint64_t n = w->pend.size();
+    w->out.resize(fb200_deflate_stream_bound(n));
+    uint64_t off[2] = {0, n}, doff[2], olen = 0;
+    rc = fb200_deflate_streams(w->ctx, w->pend.data(), off, 1, w->out.data(), w->out.size(), doff, &olen);
+    if (rc == FB200_OK && writer_deliver(w, w->out.data(), olen) != 0) rc = FB200_ERR_ARG;
+  } else {
+    rc = writer_emit(w, w->pend.data(), w->pend.size(), true);
+  }
   if (rc != FB200_OK) { w->sticky = rc; return rc; }
-  if (w->sink(w->user, out.data(), olen) != 0) { w->sticky = FB200_ERR_ARG; return w->sticky; }
   w->closed = true;
-  std::vector<uint8_t>().swap(w->buf);
+  std::vector<uint8_t>().swap(w->pend);
+  std::vector<uint8_t>().swap(w->stage);
+  std::vector<uint8_t>().swap(w->out);
   return FB200_OK;
 }
 
-extern "C" void fb200_writer_free(fb200_writer *w) { delete w; }
+extern "C" uint64_t fb200_writer_pending(const fb200_writer *w) { return w ? w->outq.size() : 0; }
+
+extern "C" uint64_t fb200_writer_take(fb200_writer *w, uint8_t *dst, uint64_t cap)
+{
+  if (!w || (!dst && cap)) return 0;
+  const uint64_t k = w->outq.size() < cap ? w->outq.size() : cap;
+  if (k) {
+    memcpy(dst, w->outq.data(), k);
+    w->outq.erase(w->outq.begin(), w->outq.begin() + (ptrdiff_t)k);
+  }
+  return k;
+}
+
+extern "C" void fb200_writer_free(fb200_writer *w)
+{
+  if (!w) return;
+  if (w->d_seed) {
+    cudaSetDevice(w->ctx->device);
+    cudaFree(w->d_seed);
+  }
+  delete w;
+}
 
 // Streaming Decompressor (inflate.mbt:257-418).  The first read inflates the
 // whole stream on the GPU; reads then hand the result out with the
@@ -1384,7 +1527,7 @@ struct fb200_reader {
   std::vector<uint8_t> dict; // &Reader::new_dict / Decompressor::reset: the last <= 32768 bytes of the dictionary
   bool decoded = false;
   std::vector<uint8_t> out;
-  uint64_t total = 0, pos = 0;
+  uint64_t total = 0, pos = 0, consumed = 0;
   int32_t status = -1;
   int64_t err_off = 0;
   int rc = FB200_OK;
@@ -1467,8 +1610,10 @@ static void reader_decode(fb200_reader *r)
       uint64_t olen = 0;
       int32_t st = -1;
       int64_t eo = 0;
+      uint64_t cons = 0;
       r->rc = fb200_inflate_dict(r->ctx, r->comp, r->n, r->dict.data(), r->dict.size(), r->out.data(), cap, &olen, &st,
-                                 &eo, nullptr);
+                                 &eo, &cons);
+      r->consumed = cons;
       if (r->rc != FB200_OK) { r->status = FB200_ST_INTERNAL; r->total = 0; return; }
       if (st == FB200_ST_DST_TOO_SMALL && cap < r->n * 1040 + 65536) { cap *= 4; continue; }
       r->total = olen;
@@ -1489,6 +1634,7 @@ static void reader_decode(fb200_reader *r)
     r->total = olen;
     r->status = st;
     r->err_off = eo;
+    r->consumed = cons;
     return;
   }
 }
@@ -1519,7 +1665,7 @@ extern "C" int fb200_reader_reset(fb200_reader *r, const uint8_t *comp, uint64_t
   r->comp = comp;
   r->n = n;
   r->decoded = false;
-  r->total = r->pos = 0;
+  r->total = r->pos = r->consumed = 0;
   r->status = -1;
   r->err_off = 0;
   r->rc = FB200_OK;
@@ -1553,6 +1699,13 @@ extern "C" uint64_t fb200_reader_read(fb200_reader *r, uint8_t *buf, uint64_t n,
     if (err_off) *err_off = r->err_off;
   }
   return k;
+}
+
+extern "C" uint64_t fb200_reader_consumed(fb200_reader *r)
+{
+  if (!r) return 0;
+  if (!r->decoded) reader_decode(r);
+  return r->consumed;
 }
 
 extern "C" int fb200_reader_close(fb200_reader *r)

@@ -40,6 +40,7 @@ __host__ __device__ inline bool block_resets_table(uint64_t b)
 constexpr int kKindStored = 0;   // n <= 16
 constexpr int kKindHuff = 1;     // 17 <= n <= 127, or tokens > n - n/16
 constexpr int kKindDynamic = 2;
+constexpr int kKindSkip = 3;     // stand-in block of a continued stream (DeflateJob::cont_prev): no bits
 
 // per-block header scratch: 14 + 19*3 + 316 * (7 + 7) bits worst case < 4608 bits
 constexpr int kHdrWords = 160;

@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(256) k_histogram(DeflateJob j)
   const uint32_t n = r.n;
   const uint32_t ntok = j.blk_ntok[blk];
   int kind;
-  if (n <= 16) kind = kKindStored;                 // deflate.mbt:248-249
+  if (j.cont_prev && blk == 0) kind = kKindSkip;   // stand-in for the part of the stream earlier calls compressed
+  else if (n <= 16) kind = kKindStored;            // deflate.mbt:248-249
   else if (n < 128) kind = kKindHuff;              // :250-252
   else kind = (ntok > n - (n >> 4)) ? kKindHuff : kKindDynamic; // :266
   for (int i = threadIdx.x; i < kFreqStride; i += blockDim.x) hist[i] = 0;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_build_codes(DeflateJob j, uin
     if (j.blk_begin + b32 >= j.blk_end) break;
     const uint64_t blk = j.blk_begin + b32;
     const int kind = j.blk_kind[blk];
-    if (kind == kKindStored) continue;
+    if (kind == kKindStored || kind == kKindSkip) continue;
     const uint32_t *gfreq = j.blk_freq + blk * kFreqStride;
     if (NS < kMaxSyms) { // small pass: count the literal/length symbols in use
       int used = 0;
@@ -165,9 +166,10 @@ __global__ void k_layout(DeflateJob j)
   if (st >= j.st_end) return;
   const uint64_t b0 = j.stream_blk0[st], b1 = j.stream_blk0[st + 1];
   const uint64_t L = j.stream_off[st + 1] - j.stream_off[st];
-  uint64_t bit = 0;
+  uint64_t bit = j.cont_start_bit; // (0 unless the stream continues one of an earlier call: single-stream calls)
   for (uint64_t b = b0; b < b1; b++) {
     j.blk_bit_start[b] = bit;
+    if (j.blk_kind[b] == kKindSkip) continue;
     if (j.blk_kind[b] == kKindStored) {
       const uint64_t boff = (b - b0) * (uint64_t)kBlockSize;
       const uint64_t n = (L - boff) < (uint64_t)kBlockSize ? (L - boff) : (uint64_t)kBlockSize;
@@ -177,6 +179,10 @@ __global__ void k_layout(DeflateJob j)
     }
   }
   j.stream_trailer_bit[st] = bit;
+  if (j.cont_open) { // more data follows: no final block; the last byte may be partial
+    j.stream_bytes[st] = (bit + 7) >> 3;
+    return;
+  }
   bit = ((bit + 3 + 7) & ~7ull) + 32; // final empty stored block (deflate.mbt:171)
   j.stream_bytes[st] = bit >> 3;
 }
@@ -228,6 +234,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(DeflateJob j)
   if (j.dst_off[j.st_end] > j.dst_cap) return; // the range does not fit: nothing is written, the host reports the need
   const BlockRef r = block_ref(j, blk);
   const int kind = j.blk_kind[blk];
+  if (kind == kKindSkip) return;
   uint32_t *dst32 = reinterpret_cast<uint32_t *>(j.dst);
   const uint64_t B0 = j.dst_off[r.st] * 8 + j.blk_bit_start[blk];
   const uint8_t *src = j.src + r.src_off;
@@ -358,7 +365,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(DeflateJob j)
 __global__ void k_trailer(DeflateJob j)
 {
   const uint64_t st = j.st_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (st >= j.st_end || j.dst_off[j.st_end] > j.dst_cap) return;
+  if (st >= j.st_end || j.dst_off[j.st_end] > j.dst_cap || j.cont_open) return;
   uint32_t *dst32 = reinterpret_cast<uint32_t *>(j.dst);
   const uint64_t bit = j.dst_off[st] * 8 + j.stream_trailer_bit[st];
   atomicOr(&dst32[bit >> 5], 1u << (bit & 31));

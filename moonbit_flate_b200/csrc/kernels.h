@@ -41,6 +41,15 @@ struct DeflateJob {
   uint64_t dst_cap;              // K4 writes nothing for a range that would end beyond it (host reports the need)
   // output
   uint8_t *dst;
+  // Continuation of ONE stream across calls (the streaming Writer: every call compresses the full 65535-byte
+  // windows that have arrived, the hash table and the bit position carry over).  The call then holds a single
+  // stream.  cont_prev: its first block is a stand-in for what came before -- only its last 32768 bytes are real
+  // (the history a 4-byte candidate check may read, D1) -- it is never parsed and emits nothing, and the block
+  // behind it is seeded with the end table the previous call left.  cont_open: more data follows, so the final
+  // empty stored block is not written and the end table of the last block is kept.
+  uint32_t cont_prev, cont_open;
+  uint32_t cont_start_bit;  // bits of the first output byte that the previous call has used already (0..7)
+  uint64_t cont_block_base; // cont_prev: block b >= 1 of this call is block cont_block_base + b - 1 of the whole stream (table resets)
 };
 constexpr int kFreqStride = 320;
 
@@ -59,6 +68,9 @@ struct BlockParJob {
   uint8_t *lat_next;       // [nmb]
   uint8_t *chg_next;       // [nmb] the block's end table changed in this round
   int round;
+  // DeflateJob::cont_prev / cont_open / cont_block_base of the call (see there)
+  uint32_t cont_prev, cont_open;
+  uint64_t cont_block_base;
 };
 
 // one-time device tables (probe schedule); call once per context
@@ -81,6 +93,8 @@ void launch_bp_round(const DeflateJob &j, const BlockParJob &bp, const uint8_t *
                      cudaStream_t st);
 void launch_parse_blocks(const DeflateJob &j, const BlockParJob &bp, uint32_t *counter, int num_sms, void *gtables,
                          cudaStream_t st);
+// continuation: the latest end table of multi-block-stream block m -> out (1 << 14 uint16), after the last round
+void launch_bp_save_table(const BlockParJob &bp, uint64_t m, const uint8_t *lat, uint16_t *out, cudaStream_t st);
 // K2: block kind + histograms (huffman-bit-writer.mbt:550-593, :831)
 void launch_histogram(const DeflateJob &j, cudaStream_t st);
 // K3: code construction + codegen + header + sizes (huffman-code.mbt:112-343,

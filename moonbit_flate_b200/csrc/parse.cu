@@ -128,7 +128,11 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
     const uint64_t blk0 = j.stream_blk0[st32];
     const uint32_t nblk = (uint32_t)((L + kBlockSize - 1) / kBlockSize);
     const uint32_t bp_b = (MULTI && bp) ? (uint32_t)(bp_gb - blk0) : 0u;
-    const bool bp_seed = MULTI && bp && bp->round > 1 && bp_b > 0 && !block_resets_table(bp_b); // round 1: empty tables
+    if (j.cont_prev && !(MULTI && bp)) continue; // a continued stream is parsed by the block-parallel rounds only
+    // round 1: empty tables -- except behind the stand-in block of a continued stream, whose end table is given
+    const uint64_t abs_b = (MULTI && bp && bp->cont_prev) ? bp->cont_block_base + bp_b - 1 : bp_b; // index in the whole stream
+    const bool bp_seed = MULTI && bp && bp_b > 0 && !block_resets_table(abs_b) &&
+                         (bp->round > 1 || (bp->cont_prev && bp_b == 1));
     if (!bp_seed) { // DeflateFast::new (:111-117): empty table
       const uint32_t fill = MULTI ? 0u : 0xffffffffu;
       uint4 *t4 = reinterpret_cast<uint4 *>(table);
@@ -403,7 +407,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
       ntok += (uint32_t)(n - next_emit);
       if (lane == 0) j.blk_ntok[blk0 + b] = ntok;
       __syncwarp();
-      if (MULTI && bp && b + 1 < nblk && L - (uint64_t)(b + 1) * kBlockSize >= 128) {
+      if (MULTI && bp && ((b + 1 < nblk && L - (uint64_t)(b + 1) * kBlockSize >= 128) || (bp->cont_open && b + 1 == nblk))) {
         // the next block is parsed too: leave it this block's end table, and note whether it differs from the
         // one the previous round left (only then the next block has to be parsed again)
         const uint64_t m = bp->mb_idx[bp_gb];
@@ -494,8 +498,20 @@ __global__ void k_bp_round(DeflateJob j, BlockParJob bp, const uint8_t *chg_prev
   const uint64_t m = bp.mb_idx[gb];
   bp.lat_next[m] = bp.round == 1 ? 0 : bp.lat_prev[m];
   bp.chg_next[m] = 0;
-  const bool need = parsed && (bp.round == 1 || (b > 0 && !block_resets_table(b) && chg_prev[m - 1]));
+  const bool need = parsed && !(bp.cont_prev && b == 0) &&
+                    (bp.round == 1 || (b > 0 && !block_resets_table(bp.cont_prev ? bp.cont_block_base + b - 1 : b) && chg_prev[m - 1]));
   if (need) list[atomicAdd(nlist, 1u)] = (uint32_t)gb;
+}
+
+__global__ void k_bp_save_table(BlockParJob bp, uint64_t m, const uint8_t *lat, uint16_t *out)
+{
+  const uint16_t *t = bp.tabs + ((size_t)lat[m] * bp.nmb + m) * kTableSize;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTableSize; i += gridDim.x * blockDim.x) out[i] = t[i];
+}
+
+void launch_bp_save_table(const BlockParJob &bp, uint64_t m, const uint8_t *lat, uint16_t *out, cudaStream_t st)
+{
+  k_bp_save_table<<<16, 256, 0, st>>>(bp, m, lat, out);
 }
 
 void launch_init_tables(cudaStream_t st) { k_init_sched<<<1, 1, 0, st>>>(); }
@@ -829,6 +845,7 @@ void preload_parse_kernels()
   cudaFuncGetAttributes(&a, k_parse_blocks);
   cudaFuncGetAttributes(&a, k_bp_flags);
   cudaFuncGetAttributes(&a, k_bp_round);
+  cudaFuncGetAttributes(&a, k_bp_save_table);
   cudaFuncGetAttributes(&a, k_count_blocks);
   cudaFuncGetAttributes(&a, k_count_multi);
   cudaFuncGetAttributes(&a, k_fill_blocks);

@@ -17,3 +17,12 @@ fb200_ctx *fb200_create_ret(int device)
   }
   return ctx;
 }
+
+/* Writer objects in their pull form (no callback crosses the FFI): the compressed bytes queue up inside the
+ * object and the MoonBit side collects them with fb200_writer_take after every write / close. */
+fb200_writer *fb200_writer_new_pull(fb200_ctx *ctx) { return fb200_writer_new(ctx, NULL, NULL); }
+
+fb200_writer *fb200_writer_new_dict_pull(fb200_ctx *ctx, const uint8_t *dict, uint64_t n)
+{
+  return fb200_writer_new_dict(ctx, NULL, NULL, dict, n);
+}

@@ -223,6 +223,94 @@ def test_writer_reader_mirror(ctx, oracle):
             assert err is None and got == want
 
 
+@pytest.mark.parametrize("klass", [0, 1, 2, 3])
+def test_writer_streams_window_by_window(ctx, oracle, corpus, klass):
+    """Compressor::write encodes every 65535-byte window the moment it is full (deflate.mbt:280-294): the Writer
+    hands the bytes of the windows a write has completed to its sink before the write returns -- whatever the
+    chunking, the concatenation is the oracle's stream (the hash table, the 32768 bytes of history for the 4-byte
+    cross-block check, the table-reset count and the bit position carry over from call to call)."""
+    import io
+
+    import moonbit_flate_b200 as fb
+
+    data = corpus.unit(5 * 65535 + 4321, seed=77, index=klass, klass=klass)
+    want = oracle.deflate(data)
+    rng = np.random.default_rng(klass)
+    patterns = [
+        [len(data)],
+        [65535] * 5 + [4321],
+        [1, 65534, 65535 * 2, 1, len(data) - 65535 * 3 - 1],
+        [3 * 65535, 2 * 65535 + 4321],
+        [5 * 65535, 4321],          # close() with a small parsed tail
+        [5 * 65535 + 4321 - 10, 10],
+    ]
+    cuts = sorted(rng.choice(len(data), 40, replace=False).tolist())
+    patterns.append([b - a for a, b in zip([0] + cuts, cuts + [len(data)])])
+    for sizes in patterns:
+        assert sum(sizes) == len(data)
+        buf = io.BytesIO()
+        w = fb.Writer.new(buf, ctx)
+        pos = 0
+        for n in sizes:
+            assert w.write(data[pos: pos + n]) == (n, None)
+            pos += n
+            if pos >= 65535:  # the completed windows have left before close
+                assert len(buf.getvalue()) > 0, sizes
+            # nothing of a window that is not full yet has been emitted: the prefix so far is a prefix of the stream
+            assert want.startswith(buf.getvalue()), sizes
+        assert w.close() is None
+        assert buf.getvalue() == want, (klass, sizes[:6])
+    # exact multiple of the window, then close with nothing pending; and a stream of one window + stored tail
+    for n in (2 * 65535, 65535, 65535 + 7, 65535 + 100, 65535 + 128):
+        d = data[:n]
+        buf = io.BytesIO()
+        w = fb.Writer.new(buf, ctx)
+        assert w.write(d[:65535]) == (65535, None)
+        assert w.write(d[65535:]) == (n - 65535, None)
+        assert w.close() is None
+        assert buf.getvalue() == oracle.deflate(d), n
+
+
+def test_writer_pull_form_and_reader_consumed(ctx, oracle, corpus):
+    """The pull form of the Writer (no callback: hosts like the MoonBit shim collect the bytes with
+    fb200_writer_take) yields the same stream; the Reader reports how much of its input the decoder consumed, so
+    that what follows the deflate stream -- a gzip / zlib trailer, the next member -- stays with the caller
+    (the reference pulls its input byte by byte and stops behind the final block, inflate.mbt:789-799)."""
+    import moonbit_flate_b200 as fb
+
+    L = fb._lib
+    data = corpus.unit(200000, seed=5, index=3, klass=0)
+    want = oracle.deflate(data)
+    w = L.fb200_writer_new(ctx._h, fb.SINK_FN(0), None)
+    assert w
+    got = bytearray()
+    buf = np.empty(1 << 16, np.uint8)
+    for a in range(0, len(data), 50000):
+        chunk = np.frombuffer(data[a: a + 50000], dtype=np.uint8)
+        assert L.fb200_writer_write(w, chunk.ctypes.data, chunk.size) == chunk.size
+        while L.fb200_writer_pending(w):
+            k = L.fb200_writer_take(w, buf.ctypes.data, buf.size)
+            got += buf[:k].tobytes()
+        if a + 50000 >= 65535:
+            assert len(got) > 0  # the first window has left with the write that completed it
+    assert L.fb200_writer_close(w) == 0
+    while L.fb200_writer_pending(w):
+        k = L.fb200_writer_take(w, buf.ctypes.data, buf.size)
+        got += buf[:k].tobytes()
+    L.fb200_writer_free(w)
+    assert bytes(got) == want
+    # consumed: exactly the deflate stream, whatever follows it
+    for tail in (b"", b"\x01\x02\x03\x04trailer", want):
+        r = fb.Reader.new(want + tail, ctx)
+        out, err = r.read_all()
+        assert err is None and out == data
+        assert r.consumed() == len(want)
+    st, _, _, cons = oracle.inflate(want[: len(want) // 2], len(data) + 1)
+    r = fb.Reader.new(want[: len(want) // 2], ctx)
+    r.read_all()
+    assert r.consumed() == cons
+
+
 def test_writer_dict_kat(ctx):
     """deflate_test.mbt:12-35: 28 bytes -> exactly 38 bytes; new_dict(dict)+write(text) == write(dict)+write(text)."""
     import io
