@@ -266,6 +266,7 @@ int fb200_debug_block_resets(uint64_t b);
  *   FB200_PARSE_BLOCKPAR=0|1|2  block-parallel parse of multi-block streams: never / when few streams / always
  *   FB200_PARSE_WARPS=s, FB200_PARSE_GWARPS=g  parse warps per SM with shared-memory / global-memory tables
  *   FB200_INFLATE_CTAS=c      inflate CTAs (4 warps each) per SM
+ *   FB200_INFLATE_CTA_STREAMS=n  calls with at most n streams inflate with one CTA per stream (296; 0: never)
  *   FB200_TRACE=1             timeline of the host-buffer calls on stderr */
 
 #ifdef __cplusplus

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -193,6 +194,9 @@ struct fb200_ctx {
   // the watermark included, between passes) need the copies to have finished before the launch, which is what
   // overlap_h2d == false selects: no watermark, the kernel is ordered behind the last chunk.
   bool overlap_h2d = true;
+  // calls with at most this many streams inflate with one CTA per stream instead of one warp per stream
+  // (FB200_INFLATE_CTA_STREAMS; 0 = always a warp per stream)
+  uint32_t cta_streams = 296;
   double t_kernels_done = 0; // FB200_TRACE=2
   // fb200_*_async: the blocking call runs on a helper thread; fb200_wait joins it (one call in flight per context)
   std::thread worker;
@@ -292,6 +296,7 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
   // FB200_HOST_OVERLAP: 1 forces the watermark overlap on, 0 off; unset = on unless a serialising tool is attached
   ctx->overlap_h2d = !serialising_tool_attached();
   if (const char *e = getenv("FB200_HOST_OVERLAP")) ctx->overlap_h2d = atoi(e) != 0;
+  if (const char *e = getenv("FB200_INFLATE_CTA_STREAMS")) ctx->cta_streams = (uint32_t)atol(e);
   if (const char *e = getenv("FB200_DEFLATE_PIPELINE")) ctx->pipeline = atoi(e) != 0;
   if (const char *e = getenv("FB200_PARSE_BLOCKPAR")) ctx->blockpar = atoi(e);
   if (const char *e = getenv("FB200_GROUP_MB")) {
@@ -1072,6 +1077,7 @@ static int inflate_launch(fb200_ctx *ctx, const uint8_t *d_comp, const uint64_t 
   j.counters = ctx->counters.as<uint32_t>();
   j.fallback = ctx->i_fallback.as<uint32_t>();
   j.avail = hk.avail;
+  j.cta_streams = ctx->cta_streams;
   j.hist0 = hk.hist0;
   j.group_done = hk.group_done;
   j.group_flag = hk.group_flag;
@@ -1336,6 +1342,7 @@ extern "C" int fb200_wait(fb200_ctx *ctx)
 
 struct fb200_writer {
   fb200_ctx *ctx;
+  int device = 0;             // (kept here: the object may be freed after its context)
   fb200_sink_fn sink;
   void *user;
   std::vector<uint8_t> pend;  // bytes written and not yet compressed (< 65535 between calls)
@@ -1365,6 +1372,7 @@ extern "C" fb200_writer *fb200_writer_new(fb200_ctx *ctx, fb200_sink_fn sink, vo
   fb200_writer *w = new (std::nothrow) fb200_writer();
   if (!w) return nullptr;
   w->ctx = ctx;
+  w->device = ctx->device;
   w->sink = sink;
   w->user = user;
   return w;
@@ -1510,8 +1518,7 @@ extern "C" void fb200_writer_free(fb200_writer *w)
 {
   if (!w) return;
   if (w->d_seed) {
-    cudaSetDevice(w->ctx->device);
-    cudaFree(w->d_seed);
+    if (cudaSetDevice(w->device) != cudaSuccess || cudaFree(w->d_seed) != cudaSuccess) cudaGetLastError();
   }
   delete w;
 }
@@ -1526,7 +1533,7 @@ struct fb200_reader {
   uint64_t n;
   std::vector<uint8_t> dict; // &Reader::new_dict / Decompressor::reset: the last <= 32768 bytes of the dictionary
   bool decoded = false;
-  std::vector<uint8_t> out;
+  std::unique_ptr<uint8_t[]> out;
   uint64_t total = 0, pos = 0, consumed = 0;
   int32_t status = -1;
   int64_t err_off = 0;
@@ -1603,32 +1610,18 @@ extern "C" int fb200_inflate_dict(fb200_ctx *ctx, const uint8_t *comp, uint64_t 
 static void reader_decode(fb200_reader *r)
 {
   r->decoded = true;
-  if (!r->dict.empty()) {
-    uint64_t cap = r->n * 8 + 65536;
-    for (;;) {
-      r->out.resize(cap);
-      uint64_t olen = 0;
-      int32_t st = -1;
-      int64_t eo = 0;
-      uint64_t cons = 0;
-      r->rc = fb200_inflate_dict(r->ctx, r->comp, r->n, r->dict.data(), r->dict.size(), r->out.data(), cap, &olen, &st,
-                                 &eo, &cons);
-      r->consumed = cons;
-      if (r->rc != FB200_OK) { r->status = FB200_ST_INTERNAL; r->total = 0; return; }
-      if (st == FB200_ST_DST_TOO_SMALL && cap < r->n * 1040 + 65536) { cap *= 4; continue; }
-      r->total = olen;
-      r->status = st;
-      r->err_off = eo;
-      return;
-    }
-  }
+  // One stream through fb200_inflate_dict (with or without a dictionary): the output comes back in one copy of exactly
+  // the bytes produced.  The capacity is a guess (a deflate stream expands at most 1032 : 1) that grows on demand;
+  // the host buffer is left uninitialised, untouched pages cost nothing.
   uint64_t cap = r->n * 8 + 65536;
   for (;;) {
-    r->out.resize(cap);
-    uint64_t coff[2] = {0, r->n}, ooff[2] = {0, cap}, olen = 0, cons = 0;
+    r->out.reset(new (std::nothrow) uint8_t[cap]);
+    if (!r->out) { r->rc = FB200_ERR_NOMEM; r->status = FB200_ST_INTERNAL; r->total = 0; return; }
+    uint64_t olen = 0, cons = 0;
     int32_t st = -1;
     int64_t eo = 0;
-    r->rc = fb200_inflate_batch(r->ctx, r->comp, coff, 1, r->out.data(), ooff, &olen, &st, &eo, &cons);
+    r->rc = fb200_inflate_dict(r->ctx, r->comp, r->n, r->dict.empty() ? nullptr : r->dict.data(), r->dict.size(), r->out.get(), cap,
+                               &olen, &st, &eo, &cons);
     if (r->rc != FB200_OK) { r->status = FB200_ST_INTERNAL; r->total = 0; return; }
     if (st == FB200_ST_DST_TOO_SMALL && cap < r->n * 1040 + 65536) { cap *= 4; continue; }
     r->total = olen;
@@ -1690,7 +1683,7 @@ extern "C" uint64_t fb200_reader_read(fb200_reader *r, uint8_t *buf, uint64_t n,
   if (chunk_end > r->total) chunk_end = r->total;
   uint64_t k = chunk_end - r->pos;
   if (k > n) k = n;
-  memcpy(buf, r->out.data() + r->pos, k);
+  memcpy(buf, r->out.get() + r->pos, k);
   r->pos += k;
   *status = -1;
   // the status rides on the read that drains the final, partial window flush (inflate.mbt:392-396)

@@ -256,7 +256,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
 // with absolute destinations.  One symbol per step and lane; the step is straight-line code, and its two
 // optional parts (a code longer than the direct table, a length/distance pair) are entered by the whole
 // warp when any lane needs them.
-template <bool WRITE>
+// RING (the CTA-per-stream kernel): `out` is a ring of kRing bytes in shared memory that holds the output by
+// absolute position modulo kRing; the copies are replayed there before the block leaves for global memory.
+constexpr uint32_t kRing = 128u * 1024u;
+constexpr uint32_t kRingMask = kRing - 1u;
+
+template <bool WRITE, bool RING = false>
 __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_len_tab, const uint32_t *s_dist_tab,
                                               const uint8_t *in, int64_t cur_len, uint32_t bend, bool run,
                                               uint32_t start, uint32_t e, uint32_t &p_out, uint32_t &flag_out,
@@ -314,10 +319,16 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
         // (the third look-up needs its 10 index bits inside the 32-bit peek: cl + c1 <= 22; that also keeps the
         // bits dropped per step <= 32, which is all LBits::drop can move in one call)
         const bool three = two && cl + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
-        if (WRITE) {
+        if (WRITE && !RING) {
           op[cnt_out] = (uint8_t)sym;
           if (two) op[cnt_out + 1] = (uint8_t)s1;
           if (three) op[cnt_out + 2] = (uint8_t)s2;
+        }
+        if (WRITE && RING) {
+          const uint32_t at = obase + cnt_out;
+          out[at & kRingMask] = (uint8_t)sym;
+          if (two) out[(at + 1u) & kRingMask] = (uint8_t)s1;
+          if (three) out[(at + 2u) & kRingMask] = (uint8_t)s2;
         }
         cnt_out += 1u + (two ? 1u : 0u) + (three ? 1u : 0u);
         lb.drop((int)(cl + (two ? c1 : 0u) + (three ? c2 : 0u)));
@@ -369,7 +380,7 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
 // The same for a block whose code has no length symbols (HLIT = 257: the literal-only blocks the encoder
 // emits for incompressible data, which resynchronise poorly and therefore run many rounds): nothing but
 // literals and EOB, up to three symbols per step.
-template <bool WRITE>
+template <bool WRITE, bool RING = false>
 __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t *in, int64_t cur_len, uint32_t bend,
                                                   bool run, uint32_t start, uint32_t e, uint32_t &p_out,
                                                   uint32_t &flag_out, uint32_t &n_out, uint8_t *out, uint32_t obase)
@@ -405,10 +416,16 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
         const uint32_t c2 = e2 & 15u, s2 = e2 >> 4;
         const uint32_t ab1 = ab0 + c1;
         const bool three = two && c0 + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
-        if (WRITE) {
+        if (WRITE && !RING) {
           op[cnt_out] = (uint8_t)s0;
           if (two) op[cnt_out + 1] = (uint8_t)s1;
           if (three) op[cnt_out + 2] = (uint8_t)s2;
+        }
+        if (WRITE && RING) {
+          const uint32_t at = obase + cnt_out;
+          out[at & kRingMask] = (uint8_t)s0;
+          if (two) out[(at + 1u) & kRingMask] = (uint8_t)s1;
+          if (three) out[(at + 2u) & kRingMask] = (uint8_t)s2;
         }
         cnt_out += 1u + (two ? 1u : 0u) + (three ? 1u : 0u);
         lb.drop((int)(c0 + (two ? c1 : 0u) + (three ? c2 : 0u)));
@@ -425,9 +442,17 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
   n_out = cnt_out;
 }
 
-// Replays records [0, nrec) of one stream in order.
-__device__ void replay_records(uint8_t *out, const uint2 *rec, uint32_t nrec, int lane)
+// Replays records [0, nrec) in order, one warp.  RING: the output lives in a shared-memory ring (position modulo
+// kRing, the CTA-per-stream kernel); otherwise `buf` is the stream's output slot in global memory.
+template <bool RING>
+__device__ void replay_records(uint8_t *buf, const uint2 *rec, uint32_t nrec, int lane)
 {
+  // positions are relative to the stream's output slot; a source may lie in front of it (preset dictionary): signed
+  auto ld = [&](int64_t pos) -> uint8_t { return RING ? buf[(uint32_t)pos & kRingMask] : __ldcg(buf + pos); };
+  auto st = [&](int64_t pos, uint8_t v) {
+    if (RING) buf[(uint32_t)pos & kRingMask] = v;
+    else buf[pos] = v;
+  };
   uint2 nxt = make_uint2(0u, 0u); // the next group's records are requested while this group is being copied
   if ((uint32_t)lane < nrec) nxt = rec[lane];
   for (uint32_t g = 0; g < nrec; g += 32) {
@@ -440,7 +465,8 @@ __device__ void replay_records(uint8_t *out, const uint2 *rec, uint32_t nrec, in
     if (r + 32u < nrec) nxt = rec[r + 32u];
     const bool big = len > (uint32_t)kLaneCopyMax;
     // source interval: [dst - dist, dst - dist + min(len, dist))
-    const uint32_t src_end = dst - dist + (len < dist ? len : dist);
+    const uint32_t src = dst - dist;
+    const uint32_t src_end = src + (len < dist ? len : dist);
     unsigned pending = __ballot_sync(kFull, r < nrec);
     while (pending) {
       const int p = __ffs(pending) - 1;
@@ -449,17 +475,16 @@ __device__ void replay_records(uint8_t *out, const uint2 *rec, uint32_t nrec, in
       if (bigp) { // the whole warp copies record p
         const uint32_t lenp = __shfl_sync(kFull, len, p);
         const uint32_t dd = __shfl_sync(kFull, dist, p);
-        uint8_t *dp = out + dstp;
-        const uint8_t *sp = dp - dd;
+        const int64_t sp = (int64_t)dstp - (int64_t)dd;
         if (dd >= 32u) {
           // pieces of at most dd bytes never read what they write; 32 bytes per step inside a piece
           for (uint32_t b0 = 0; b0 < lenp; b0 += dd) {
             const uint32_t b1 = b0 + dd < lenp ? b0 + dd : lenp;
-            for (uint32_t i = b0 + lane; i < b1; i += 32) dp[i] = __ldcg(sp + i);
+            for (uint32_t i = b0 + lane; i < b1; i += 32) st(dstp + i, ld(sp + i));
             __syncwarp();
           }
         } else { // overlapping: the pattern of dd bytes repeats (dict-decoder.mbt:136-149)
-          for (uint32_t i = lane; i < lenp; i += 32) dp[i] = __ldcg(sp + (i % dd));
+          for (uint32_t i = lane; i < lenp; i += 32) st(dstp + i, ld(sp + (i % dd)));
         }
         pending &= ~(1u << p);
         __syncwarp();
@@ -471,21 +496,37 @@ __device__ void replay_records(uint8_t *out, const uint2 *rec, uint32_t nrec, in
       const unsigned bigm = __ballot_sync(kFull, big) & pending;
       const unsigned ready = __ballot_sync(kFull, mine) & (bigm ? ((1u << (__ffs(bigm) - 1)) - 1u) : kFull);
       if ((ready >> lane) & 1u) {
-        uint8_t *dp = out + dst;
-        const uint8_t *sp = dp - dist;
-        uint8_t v[kLaneCopyMax];
-        if (dist >= len) {
+        if (RING) {
+          uint8_t v[kLaneCopyMax];
+          if (dist >= len) {
+#pragma unroll
+            for (int k = 0; k < kLaneCopyMax; k++)
+              if ((uint32_t)k < len) v[k] = buf[(src + (uint32_t)k) & kRingMask];
+          } else {
+#pragma unroll
+            for (int k = 0; k < kLaneCopyMax; k++)
+              if ((uint32_t)k < len) v[k] = buf[(src + ((uint32_t)k % dist)) & kRingMask];
+          }
 #pragma unroll
           for (int k = 0; k < kLaneCopyMax; k++)
-            if ((uint32_t)k < len) v[k] = __ldcg(sp + k);
+            if ((uint32_t)k < len) buf[(dst + (uint32_t)k) & kRingMask] = v[k];
         } else {
+          uint8_t *dp = buf + dst;
+          const uint8_t *sp = dp - dist;
+          uint8_t v[kLaneCopyMax];
+          if (dist >= len) {
+#pragma unroll
+            for (int k = 0; k < kLaneCopyMax; k++)
+              if ((uint32_t)k < len) v[k] = __ldcg(sp + k);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kLaneCopyMax; k++)
+              if ((uint32_t)k < len) v[k] = __ldcg(sp + ((uint32_t)k % dist));
+          }
 #pragma unroll
           for (int k = 0; k < kLaneCopyMax; k++)
-            if ((uint32_t)k < len) v[k] = __ldcg(sp + ((uint32_t)k % dist));
+            if ((uint32_t)k < len) dp[k] = v[k];
         }
-#pragma unroll
-        for (int k = 0; k < kLaneCopyMax; k++)
-          if ((uint32_t)k < len) dp[k] = v[k];
       }
       pending &= ~ready;
       __syncwarp();
@@ -738,7 +779,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
     if (!bail && ub.consumed_bits(in) > cur_len * 8) bail = true;
     if (!bail) {
       __syncwarp();
-      replay_records(out, rec, nrec, lane);
+      replay_records<false>(out, rec, nrec, lane);
     }
     if (lane == 0) {
       if (bail) {
@@ -768,6 +809,381 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// One CTA per stream: the same speculative decode with 32 * CW ranges per block, for calls with few (long) streams
+// -- the Reader of one big stream, a handful of files -- where a warp per stream leaves the GPU idle and the
+// stream crawls (17 blocks of a 1 MiB stream one after the other took 25 ms).  Warp 0 reads the block header and
+// builds the tables; all warps decode ranges; hand-over positions, counts and the end of the chain travel
+// through shared memory; the output of a window is assembled in a shared-memory ring -- literals written there,
+// the recorded copies replayed there by warp 0 (rounds of shared-memory latency, no barrier; a CTA-wide replay with
+// two barriers per round measured 4 x slower: the copies are a dependency chain of ~460 rounds per 64 KiB whatever
+// the number of lanes) -- and leaves for global memory in one coalesced sweep.
+#ifndef FB_CTA_WARPS
+#define FB_CTA_WARPS 16 // (<= 32: one lane per warp in the replay's reductions)
+#endif
+constexpr int CW = FB_CTA_WARPS; // warps per CTA
+constexpr int CL = CW * 32;  // ranges per block
+
+struct CtaShared {
+  Smem sm;
+  uint32_t len_tab[32], dist_tab[32];
+  uint32_t p[CL], flag[CL];
+  uint32_t wo[CW], wr[CW];
+  // block header, written by warp 0
+  int bail, final_flag, typ, lit_only, flat_code;
+  int64_t b0s;
+  uint32_t sn, sp;
+  // reductions
+  uint32_t first_bad;
+};
+
+#ifdef FB_CTA_PROF
+__device__ unsigned long long g_cta_prof[8]; // cycles of thread 0: header, rounds, write pass, replay, copy-out, other
+#define CTA_T(k) do { if (tid == 0) { const long long t__ = clock64(); prof[k] += t__ - tprev; tprev = t__; } } while (0)
+#else
+#define CTA_T(k) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(CL, 1) k_inflate_cta(InflateJob j)
+{
+  extern __shared__ __align__(16) uint8_t cta_smem[];
+  CtaShared &S = *reinterpret_cast<CtaShared *>(cta_smem);
+  uint8_t *ring = cta_smem + ((sizeof(CtaShared) + 15) & ~(size_t)15); // [kRing]
+  Smem &sm = S.sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef FB_CTA_PROF
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+  if (tid < 32) {
+    S.len_tab[tid] = c3_len_tab[tid];
+    S.dist_tab[tid] = c3_dist_tab[tid];
+  }
+  __syncthreads();
+
+  for (uint32_t st32 = blockIdx.x; st32 < j.nstreams; st32 += gridDim.x) {
+    if (j.avail) { // host-buffer call: wait until the H2D stream has delivered this stream's bytes
+      if (tid == 0)
+        while (*(volatile const uint32_t *)j.avail <= st32) __nanosleep(500);
+      __syncthreads();
+    }
+    const uint8_t *in0 = j.comp + j.comp_off[st32];
+    const uint8_t *in = in0;
+    const uint64_t in_len = j.comp_off[st32 + 1] - j.comp_off[st32];
+    uint8_t *out = j.out + j.out_off[st32];
+    const uint64_t cap64 = j.out_off[st32 + 1] - j.out_off[st32];
+    const uint32_t cap = cap64 > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)cap64;
+    uint2 *rec = j.records + j.rec_off[st32];
+    const uint32_t rec_cap = (uint32_t)(j.rec_off[st32 + 1] - j.rec_off[st32]);
+    uint32_t opos = 0;
+    const uint32_t h0 = j.hist0 ? j.hist0[st32] : 0u;
+    int64_t cur_len = (int64_t)in_len;
+    bool bail = in_len > 0x0fffffffull;
+    bool done = false;
+    uint32_t win_bits = j.window_bits ? j.window_bits : 96u * 1024u * 8u;
+    int64_t hdr_bit = 0; // bit position (relative to `in`) of the next block header
+    bool ring_ok = false; // the ring holds the 32768 bytes in front of opos (or all there is)
+
+    while (!bail && !done) {
+      // ---- block header: warp 0 (the code of the warp kernel), results through shared memory ----
+      if (warp == 0) {
+        UBits ub;
+        ub.init(in, (uint64_t)cur_len);
+        ub.refill();
+        ub.drop((int)(hdr_bit & 7)); // `in` was advanced to the byte the header starts in
+        bool hb = false;
+        ub.refill();
+        const int final_flag = (int)ub.take(1);
+        const int typ = (int)ub.take(2);
+        int lit_only = 0, flat = 0;
+        uint32_t sn = 0, sp = 0;
+        int mn1 = 0, mx1 = 0, mn2 = 0, mx2 = 0;
+        if (typ == 3) hb = true;
+        else if (typ == 0) {
+          const int64_t p = (ub.consumed_bits(in) + 7) >> 3;
+          if (p + 4 > cur_len) hb = true;
+          else {
+            sn = (uint32_t)__ldg(in + p) | ((uint32_t)__ldg(in + p + 1) << 8);
+            const uint32_t nn = (uint32_t)__ldg(in + p + 2) | ((uint32_t)__ldg(in + p + 3) << 8);
+            if (nn != ((~sn) & 0xffffu) || p + 4 + sn > cur_len || (uint64_t)opos + sn > cap) hb = true;
+            sp = (uint32_t)(p + 4);
+          }
+        } else {
+          if (typ == 1) {
+            for (int i = lane; i < 288; i += 32) sm.lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+            sm.lens[288 + lane] = 5;
+            __syncwarp();
+            warp_canon(sm.lens, 288, sm.lsorted, &sm.tl, &mn1, &mx1);
+            warp_canon(sm.lens + 288, 32, sm.dsorted, &sm.td, &mn2, &mx2);
+          } else {
+            ub.refill();
+            const int nlit = (int)ub.take(5) + 257;
+            const int ndist = (int)ub.take(5) + 1;
+            const int nclen = (int)ub.take(4) + 4;
+            if (nlit > kNumLit || ndist > kNumDist) hb = true;
+            if (!hb) {
+              lit_only = nlit == 257;
+              if (lane < 19) sm.cl_lens[lane] = 0;
+              __syncwarp();
+              for (int i = 0; i < nclen; i++) {
+                ub.refill();
+                const uint32_t v = ub.take(3);
+                if (lane == 0) sm.cl_lens[c3_code_order[i]] = (uint8_t)v;
+              }
+              __syncwarp();
+              int mnc = 0, mxc = 0;
+              if (!warp_canon(sm.cl_lens, 19, sm.dsorted, &sm.td, &mnc, &mxc)) hb = true;
+              if (!hb) {
+                warp_fill_lut(sm.cl, 7, sm.dsorted, &sm.td, mnc, mxc);
+                const int n = nlit + ndist;
+                int i = 0, prev = 0;
+                while (i < n) {
+                  ub.refill();
+                  const uint32_t e = sm.cl[ub.peek() & 127];
+                  const int len = (int)(e & 15), x = (int)(e >> 4);
+                  if (len == 0) { hb = true; break; }
+                  ub.drop(len);
+                  if (x < 16) {
+                    if (lane == 0) sm.lens[i] = (uint8_t)x;
+                    prev = x;
+                    i++;
+                    continue;
+                  }
+                  int rep, b = 0;
+                  if (x == 16) {
+                    if (i == 0) { hb = true; break; }
+                    b = prev;
+                    rep = 3 + (int)ub.take(2);
+                  } else if (x == 17) rep = 3 + (int)ub.take(3);
+                  else rep = 11 + (int)ub.take(7);
+                  if (i + rep > n) { hb = true; break; }
+                  for (int k = lane; k < rep; k += 32) sm.lens[i + k] = (uint8_t)b;
+                  i += rep;
+                  prev = b;
+                }
+                __syncwarp();
+              }
+              if (!hb) {
+                uint8_t dl = 0;
+                if (lane < ndist) dl = sm.lens[nlit + lane];
+                __syncwarp();
+                sm.lens[288 + lane] = (lane < ndist) ? dl : 0;
+                __syncwarp();
+                if (sm.lens[kEob] == 0) hb = true;
+                if (!hb && !warp_canon(sm.lens, nlit, sm.lsorted, &sm.tl, &mn1, &mx1)) hb = true;
+                if (!hb && !warp_canon(sm.lens + 288, ndist, sm.dsorted, &sm.td, &mn2, &mx2)) hb = true;
+              }
+            }
+          }
+          if (!hb) {
+            warp_fill_lut(sm.lit, kLB, sm.lsorted, &sm.tl, mn1, mx1);
+            warp_fill_lut(sm.dist, kDB, sm.dsorted, &sm.td, mn2, mx2);
+            const uint32_t c = lane < 16 ? sm.tl.count[lane] : 0u;
+            const uint32_t mxc = __reduce_max_sync(kFull, c), tot = __reduce_add_sync(kFull, c);
+            flat = mxc * 10u >= tot * 8u;
+          }
+        }
+        if (lane == 0) {
+          S.bail = hb ? 1 : 0;
+          S.final_flag = final_flag;
+          S.typ = typ;
+          S.lit_only = lit_only;
+          S.flat_code = flat;
+          S.b0s = ub.consumed_bits(in);
+          S.sn = sn;
+          S.sp = sp;
+        }
+      }
+      __syncthreads();
+      CTA_T(0);
+      if (S.bail) { bail = true; break; }
+      const int final_flag = S.final_flag, typ = S.typ;
+      const bool lit_only = S.lit_only != 0, flat_code = S.flat_code != 0;
+      if (typ == 0) { // stored block (data_block / copy_data, inflate.mbt:708-766)
+        const uint32_t sn = S.sn, sp = S.sp;
+        for (uint32_t i = tid; i < sn; i += CL) out[opos + i] = __ldg(in + sp + i);
+        opos += sn;
+        ring_ok = false;
+        cur_len -= (int64_t)sp + sn;
+        in += sp + sn;
+        hdr_bit = 0;
+        __syncthreads();
+        if (final_flag) done = true;
+        continue;
+      }
+      // ---- block body: CL ranges, speculative starts, fixpoint over the hand-over positions ----
+      const int64_t b0s = S.b0s;
+      if (b0s >= cur_len * 8) { bail = true; break; }
+      uint32_t b0 = (uint32_t)b0s;
+      const uint32_t bend = (uint32_t)(cur_len * 8), blk_first_bit = b0;
+      uint32_t eob = 0;
+      for (bool have_eob = false; !have_eob && !bail;) {
+        const uint32_t wend = (uint64_t)b0 + win_bits < bend ? b0 + win_bits : bend;
+        uint32_t R = (wend - b0 + (uint32_t)CL - 1u) / (uint32_t)CL;
+        if (R < kMinRange) R = kMinRange;
+        const uint64_t s64 = (uint64_t)b0 + (uint64_t)tid * R;
+        const uint32_t s_nom = s64 < wend ? (uint32_t)s64 : wend;
+        const uint32_t e_i = (s64 + R < wend) ? (uint32_t)(s64 + R) : wend;
+        uint32_t start = s_nom, p = 0, flag = P_OK, n_out = 0, n_rec = 0;
+        if (!flat_code && e_i - s_nom > kSyncBits) start = e_i - kSyncBits;
+        bool need = true;
+        for (int round = 0; round < CL + 2; round++) {
+          uint32_t tp, tf, to, tr = 0;
+          if (lit_only) decode_ranges_lit<false>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u);
+          else decode_ranges<false>(sm, S.len_tab, S.dist_tab, in, cur_len, bend, need, start, e_i, tp, tf, to, tr, nullptr, 0u, nullptr);
+          if (need) { p = tp; flag = tf; n_out = to; n_rec = tr; }
+          S.p[tid] = p;
+          S.flag[tid] = flag;
+          __syncthreads();
+          const uint32_t pp = tid ? S.p[tid - 1] : 0u, pf = tid ? S.flag[tid - 1] : P_OK;
+          const uint32_t ns = tid == 0 ? b0 : (pf == P_OK ? pp : start);
+          need = ns != start;
+          start = ns;
+          if (!__syncthreads_or(need ? 1 : 0)) break;
+        }
+        CTA_T(1);
+        // the chain is valid up to the first range that does not hand over: it must have met EOB
+        if (tid == 0) S.first_bad = 0xffffffffu;
+        __syncthreads();
+        if (flag != P_OK) atomicMin(&S.first_bad, (uint32_t)tid);
+        __syncthreads();
+        const uint32_t fb = S.first_bad;
+        uint32_t f = CL - 1;
+        if (fb == 0xffffffffu) {
+          if (wend >= bend) { bail = true; break; } // no EOB before the end of the input
+        } else {
+          f = fb;
+          if (S.flag[f] != P_EOB) { bail = true; break; }
+        }
+        const bool mine = (uint32_t)tid <= f;
+        // CTA-wide exclusive scan of the output bytes / records of the ranges
+        uint32_t xo = mine ? n_out : 0u, xr = mine ? n_rec : 0u;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t yo = __shfl_up_sync(kFull, xo, o), yr = __shfl_up_sync(kFull, xr, o);
+          if (lane >= o) { xo += yo; xr += yr; }
+        }
+        if (lane == 31) { S.wo[warp] = xo; S.wr[warp] = xr; }
+        __syncthreads();
+        uint32_t base_o = 0, base_r = 0, tot_o = 0, tot_r = 0;
+#pragma unroll
+        for (int w = 0; w < CW; w++) {
+          if (w < warp) { base_o += S.wo[w]; base_r += S.wr[w]; }
+          tot_o += S.wo[w];
+          tot_r += S.wr[w];
+        }
+        if (tot_o > cap - opos || tot_r > rec_cap) { bail = true; break; }
+        // The output of the window is assembled in the shared-memory ring if it leaves room for the 32768 bytes of
+        // history (every window of a 65535-byte block does): literals are written there, the copies are replayed
+        // there, and the finished bytes leave for global memory in one coalesced sweep.  Otherwise in place.
+        const bool use_ring = tot_o <= kRing - (uint32_t)kMaxMatchOffset;
+        if (use_ring && !ring_ok) { // bring the history in (first block, or the previous one went another way)
+          const int64_t avail = (int64_t)opos + (int64_t)h0;
+          const uint32_t hist = avail < (int64_t)kMaxMatchOffset ? (uint32_t)avail : (uint32_t)kMaxMatchOffset;
+          for (uint32_t i = tid; i < hist; i += CL) ring[(opos - hist + i) & kRingMask] = out[(int64_t)opos - (int64_t)hist + (int64_t)i];
+          __syncthreads();
+        }
+        {
+          uint32_t tp, tf, to, tr = 0;
+          const uint32_t my_o = opos + base_o + xo - (mine ? n_out : 0u);
+          uint2 *my_rec = rec + base_r + xr - (mine ? n_rec : 0u);
+          if (use_ring) {
+            if (lit_only) decode_ranges_lit<true, true>(sm, in, cur_len, bend, mine, start, e_i, tp, tf, to, ring, my_o);
+            else decode_ranges<true, true>(sm, S.len_tab, S.dist_tab, in, cur_len, bend, mine, start, e_i, tp, tf, to, tr, ring, my_o, my_rec, h0);
+          } else {
+            if (lit_only) decode_ranges_lit<true>(sm, in, cur_len, bend, mine, start, e_i, tp, tf, to, out, my_o);
+            else decode_ranges<true>(sm, S.len_tab, S.dist_tab, in, cur_len, bend, mine, start, e_i, tp, tf, to, tr, out, my_o, my_rec, h0);
+          }
+          const bool bad = mine && (tf == P_BAD || tp != p || to != n_out || tr != n_rec);
+          if (!use_ring) __threadfence_block();
+          if (__syncthreads_or(bad ? 1 : 0)) { bail = true; break; }
+        }
+        CTA_T(2);
+        // the copies of this window, in order (everything in front of it is final)
+        if (use_ring) {
+          if (warp == 0) replay_records<true>(ring, rec, tot_r, lane);
+          __syncthreads();
+          CTA_T(3);
+          const bool al = (reinterpret_cast<uintptr_t>(out + opos) & 3u) == 0u && (opos & 3u) == 0u;
+          if (al) { // words where the two sides are aligned alike (the ring is indexed by position)
+            const uint32_t nw = tot_o >> 2;
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(ring);
+            uint32_t *ow = reinterpret_cast<uint32_t *>(out + opos);
+            for (uint32_t i = tid; i < nw; i += CL) ow[i] = rw[((opos >> 2) + i) & (kRingMask >> 2)];
+            for (uint32_t i = (nw << 2) + tid; i < tot_o; i += CL) out[opos + i] = ring[(opos + i) & kRingMask];
+          } else {
+            for (uint32_t i = tid; i < tot_o; i += CL) out[opos + i] = ring[(opos + i) & kRingMask];
+          }
+          ring_ok = true;
+        } else {
+          if (warp == 0) replay_records<false>(out, rec, tot_r, lane);
+          __threadfence_block();
+          ring_ok = false;
+        }
+        __syncthreads();
+        CTA_T(4);
+        opos += tot_o;
+        const uint32_t pend = S.p[f];
+        if (fb == 0xffffffffu) {
+          if (pend <= b0 || pend >= bend) { bail = true; break; }
+          b0 = pend; // the block goes on behind the window, which doubles: the guess was too small
+          if (win_bits < 0x40000000u) win_bits *= 2u;
+        } else {
+          eob = pend;
+          have_eob = true;
+        }
+        __syncthreads(); // S.p / S.flag are rewritten by the next window
+      }
+      if (bail) break;
+      {
+        const uint64_t w = ((uint64_t)(eob - blk_first_bit) * 5u) >> 2;
+        const uint32_t wmin = 24u * 1024u * 8u;
+        win_bits = w < wmin ? wmin : (w > 0x7fffffffull ? 0x7fffffffu : (uint32_t)w);
+        if (j.window_bits == 0xffffffffu) win_bits = 0xffffffffu;
+      }
+      if ((int64_t)eob > cur_len * 8) { bail = true; break; }
+      in += eob >> 3;
+      cur_len -= (int64_t)(eob >> 3);
+      hdr_bit = (int64_t)(eob & 7u);
+      if (final_flag) done = true;
+      __syncthreads(); // the tables are rebuilt by warp 0
+    }
+
+    // bits consumed: the stream ends hdr_bit bits into `in` (0 after a stored block: byte aligned)
+    if (!bail && ((int64_t)(in - in0) * 8 + hdr_bit > (int64_t)in_len * 8)) bail = true;
+    if (tid == 0) {
+      if (bail) {
+        const uint32_t k = atomicAdd(&j.counters[2], 1u);
+        j.fallback[k] = st32;
+      } else {
+        j.out_len[st32] = opos;
+        j.status[st32] = FB200_ST_EOF;
+        j.err_off[st32] = 0;
+        if (j.consumed) j.consumed[st32] = (uint64_t)((int64_t)(in - in0) + ((hdr_bit + 7) >> 3));
+      }
+    }
+    __syncthreads();
+    CTA_T(5);
+#ifdef FB_CTA_PROF
+    if (tid == 0)
+      for (int k = 0; k < 8; k++) { atomicAdd(&g_cta_prof[k], (unsigned long long)prof[k]); prof[k] = 0; }
+#endif
+    if (j.group_done) { // host-buffer call: publish finished output groups so their D2H copy can start
+      __threadfence();
+      if (tid == 0) {
+        const uint32_t g = st32 / j.group_streams;
+        const uint32_t first = g * j.group_streams;
+        const uint32_t cnt = (uint32_t)(j.nstreams - first < j.group_streams ? j.nstreams - first : j.group_streams);
+        if (atomicAdd(&j.group_done[g], 1u) + 1u == cnt) {
+          __threadfence_system();
+          j.group_flag[g] = 1u;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr size_t kCtaSmemBytes = ((sizeof(CtaShared) + 15) & ~(size_t)15) + kRing;
 
 } // namespace par
 
@@ -856,6 +1272,12 @@ void launch_inflate3(const InflateJob &j_in, int num_sms, cudaStream_t st)
   inflate3_config();
   if (g_win_kb == 0) j.window_bits = 0xffffffffu;
   else if (g_win_kb > 0) j.window_bits = (uint32_t)(g_win_kb * 8192);
+  // few streams: a CTA per stream (32 * 8 ranges per block) instead of a warp per stream
+  if (j.nstreams <= (uint64_t)j.cta_streams) {
+    const unsigned g = (unsigned)j.nstreams;
+    par::k_inflate_cta<<<g, par::CL, par::kCtaSmemBytes, st>>>(j);
+    return;
+  }
   const int minb = g_minb;
   const uint64_t want = (j.nstreams + par::kWarps - 1) / par::kWarps;
   const uint64_t maxg = (uint64_t)num_sms * minb;
@@ -866,6 +1288,14 @@ void launch_inflate3(const InflateJob &j_in, int num_sms, cudaStream_t st)
   else if (minb == 8) par::k_inflate_par<8><<<g, par::kWarps * 32, 0, st>>>(j);
   else par::k_inflate_par<12><<<g, par::kWarps * 32, 0, st>>>(j);
 }
+
+#ifdef FB_CTA_PROF
+extern "C" void fb200_debug_cta_prof(unsigned long long *out, int reset)
+{
+  cudaMemcpyFromSymbol(out, par::g_cta_prof, 64);
+  if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(par::g_cta_prof, z, 64); }
+}
+#endif
 
 #ifdef FB_INFLATE_STEPSTAT
 extern "C" void fb200_debug_stepstat(unsigned long long *out)
@@ -883,6 +1313,8 @@ void preload_inflate3_kernels()
   cudaFuncGetAttributes(&a, par::k_inflate_par<6>);
   cudaFuncGetAttributes(&a, par::k_inflate_par<8>);
   cudaFuncGetAttributes(&a, par::k_inflate_par<12>);
+  cudaFuncSetAttribute(par::k_inflate_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)par::kCtaSmemBytes);
+  cudaFuncGetAttributes(&a, par::k_inflate_cta);
   cudaFuncGetAttributes(&a, k_rec_off);
   cudaFuncGetAttributes(&a, k_order_count);
   cudaFuncGetAttributes(&a, k_order_scan);

@@ -156,6 +156,7 @@ struct InflateJob {
   uint32_t *nrec;           // [nstreams] records written (0: nothing to copy, or stream handed to the exact kernel)
   const uint32_t *order;    // [nstreams] decode order (largest compressed size first)
   uint32_t window_bits;     // inflate3: speculation window of a stream's first block (0: the library's default)
+  uint32_t cta_streams;     // calls with at most this many streams decode with one CTA per stream (256 ranges per block)
   // preset dictionary (&Reader::new_dict, inflate.mbt:310-317; DictDecoder::new, dict-decoder.mbt:42-60): hist0[i]
   // bytes of history (<= 32768) lie directly in front of stream i's output slot; back-references may reach into
   // them (dist > hist_size is the reference's only limit, inflate.mbt:677).  Null: no dictionaries.
