@@ -192,9 +192,12 @@ struct UBits {
   }
 };
 
-// Per-lane bit reader: a 64-bit window (hi:lo) with bit offset bo < 32 exposes >= 33 valid bits, enough for a
-// code with its extra bits; the word after the window is requested one step ahead.  Positions are 32-bit
-// word indices from the aligned word at or below the first byte (the base pointer is warp-uniform).
+// Per-lane bit reader: a 96-bit window (lo, hi, nx) with bit offset bo.  A decode step peeks at bo < 32 (32 valid
+// bits), may peek once more further in (peek_at: offsets < 64, still 32 valid bits) and moves bo with skip();
+// norm() at the end of the step brings bo back below 32 -- one refill per step for the whole warp instead of one
+// per consumed code, which matters because with 32 lanes in different places the refill branch is taken by some
+// lane at nearly every step.  Positions are 32-bit word indices from the aligned word at or below the first
+// byte (the base pointer is warp-uniform).
 struct LBits {
   const uint32_t *base;
   uint32_t nwords; // words that may be read
@@ -211,11 +214,16 @@ struct LBits {
     bo = (int)(abit & 31u);
     lo = ld(wi); hi = ld(wi + 1); nx = ld(wi + 2);
   }
-  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bo); }
-  __device__ __forceinline__ void drop(int n)
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bo); } // bo < 32
+  __device__ __forceinline__ uint32_t peek_at(int b) const // b < 64 (the funnel shift takes b modulo 32)
   {
-    bo += n;
-    if (bo >= 32) {
+    const bool up = b >= 32;
+    return __funnelshift_r(up ? hi : lo, up ? nx : hi, b);
+  }
+  __device__ __forceinline__ void skip(int n) { bo += n; }
+  __device__ __forceinline__ void norm()
+  {
+    while (bo >= 32) {
       lo = hi; hi = nx;
       wi++;
       nx = ld(wi + 2);
@@ -261,13 +269,19 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
 constexpr uint32_t kRing = 128u * 1024u;
 constexpr uint32_t kRingMask = kRing - 1u;
 
-template <bool WRITE, bool RING = false>
+// STAGE (with WRITE = false): a counting pass that also keeps what it decodes -- literals at out[position
+// relative to the lane's start] (the lane's slot of cap_lit bytes), back-references in rec[] (the lane's slot of
+// cap_rec records) with relative destinations; a lane whose slot is too small goes on counting and says so in
+// *ovf.  When no lane overflowed the block is finished by copying the slots into place, without a second decode.
+template <bool WRITE, bool RING = false, bool STAGE = false>
 __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_len_tab, const uint32_t *s_dist_tab,
                                               const uint8_t *in, int64_t cur_len, uint32_t bend, bool run,
                                               uint32_t start, uint32_t e, uint32_t &p_out, uint32_t &flag_out,
                                               uint32_t &n_out, uint32_t &n_rec, uint8_t *out, uint32_t obase,
-                                              uint2 *rec, uint32_t h0 = 0)
+                                              uint2 *rec, uint32_t h0 = 0, uint32_t cap_lit = 0, uint32_t cap_rec = 0,
+                                              bool *ovf = nullptr)
 {
+  bool over = false;
   const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(sm.lit);
   const uint32_t dist_sa = (uint32_t)__cvta_generic_to_shared(sm.dist);
   const uint32_t ltab_sa = (uint32_t)__cvta_generic_to_shared(s_len_tab);
@@ -316,8 +330,7 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
         const uint32_t e2 = lds_u16(lit_sa + (((bits >> (cl + c1)) & ((1u << kLB) - 1u)) << 1));
         const uint32_t c2 = e2 & 15u, s2 = e2 >> 4;
         const uint32_t ab1 = ab0 + c1;
-        // (the third look-up needs its 10 index bits inside the 32-bit peek: cl + c1 <= 22; that also keeps the
-        // bits dropped per step <= 32, which is all LBits::drop can move in one call)
+        // (the third look-up needs its 10 index bits inside the 32-bit peek: cl + c1 <= 22)
         const bool three = two && cl + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
         if (WRITE && !RING) {
           op[cnt_out] = (uint8_t)sym;
@@ -330,16 +343,23 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
           if (two) out[(at + 1u) & kRingMask] = (uint8_t)s1;
           if (three) out[(at + 2u) & kRingMask] = (uint8_t)s2;
         }
+        if (STAGE) {
+          if (cnt_out + 3u <= cap_lit) {
+            op[cnt_out] = (uint8_t)sym;
+            if (two) op[cnt_out + 1] = (uint8_t)s1;
+            if (three) op[cnt_out + 2] = (uint8_t)s2;
+          } else over = true;
+        }
         cnt_out += 1u + (two ? 1u : 0u) + (three ? 1u : 0u);
-        lb.drop((int)(cl + (two ? c1 : 0u) + (three ? c2 : 0u)));
+        lb.skip((int)(cl + (two ? c1 : 0u) + (three ? c2 : 0u)));
       } else {
-        lb.drop((int)adv);
+        lb.skip((int)adv); // <= 20 bits: the distance below is still inside the window
         if (sym == 256u) { flag = P_EOB; act = false; }
       }
     }
     if (__any_sync(kFull, is_len && act)) {
       if (is_len && act) {
-        const uint32_t dbits = lb.peek();
+        const uint32_t dbits = lb.peek_at(lb.bo);
         uint32_t d = lds_u16(dist_sa + ((dbits & ((1u << kDB) - 1u)) << 1));
         if (d == 0) d = canon_long(dbits, kDB + 1, &sm.td, sm.dsorted);
         if (d == 0 || (d >> 4) >= (uint32_t)kNumDist) { flag = P_BAD; act = false; }
@@ -347,18 +367,24 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
           const uint32_t dl = d & 15u;
           const uint32_t dt = lds_u32(dtab_sa + ((d >> 4) << 2));
           const uint32_t dxb = dt >> 16;
-          lb.drop((int)(dl + dxb));
+          lb.skip((int)(dl + dxb));
           if (WRITE) {
             const uint32_t dist = (dt & 0xffffu) + ((dbits >> dl) & ((1u << dxb) - 1u));
             const uint32_t at = obase + cnt_out;
             if (dist > at + h0) { flag = P_BAD; act = false; } // dist > hist_size (inflate.mbt:677), h0 = dictionary
             else rec[cnt_rec] = make_uint2(at, length | ((dist - 1u) << 16));
           }
+          if (STAGE) { // (dist > hist_size is checked when the records are moved into place)
+            const uint32_t dist = (dt & 0xffffu) + ((dbits >> dl) & ((1u << dxb) - 1u));
+            if (cnt_rec < cap_rec) rec[cnt_rec] = make_uint2(cnt_out, length | ((dist - 1u) << 16));
+            else over = true;
+          }
           cnt_out += length;
           cnt_rec++;
         }
       }
     }
+    lb.norm();
     if (act) {
       const uint32_t ab = lb.abit();
       if (ab > bend_abs) { flag = P_BAD; act = false; } // ran past the end of the input
@@ -375,16 +401,19 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
   flag_out = flag;
   n_out = cnt_out;
   n_rec = cnt_rec;
+  if (STAGE) *ovf = over;
 }
 
 // The same for a block whose code has no length symbols (HLIT = 257: the literal-only blocks the encoder
 // emits for incompressible data, which resynchronise poorly and therefore run many rounds): nothing but
 // literals and EOB, up to three symbols per step.
-template <bool WRITE, bool RING = false>
+template <bool WRITE, bool RING = false, bool STAGE = false>
 __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t *in, int64_t cur_len, uint32_t bend,
                                                   bool run, uint32_t start, uint32_t e, uint32_t &p_out,
-                                                  uint32_t &flag_out, uint32_t &n_out, uint8_t *out, uint32_t obase)
+                                                  uint32_t &flag_out, uint32_t &n_out, uint8_t *out, uint32_t obase,
+                                                  uint32_t cap_lit = 0, bool *ovf = nullptr)
 {
+  bool over = false;
   const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(sm.lit);
   const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
   const uint32_t *wbase = reinterpret_cast<const uint32_t *>(in - lead);
@@ -404,7 +433,7 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
     if (act) {
       const uint32_t c0 = e0 & 15u, s0 = e0 >> 4;
       if (e0 == 0 || s0 > 256u) { flag = P_BAD; act = false; }
-      else if (s0 == 256u) { lb.drop((int)c0); flag = P_EOB; act = false; }
+      else if (s0 == 256u) { lb.skip((int)c0); flag = P_EOB; act = false; }
       else {
         // second symbol from the same 32-bit peek, if the first one leaves the lane inside its range and the
         // second is a literal of the direct table (anything else waits for the next step)
@@ -427,10 +456,18 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
           if (two) out[(at + 1u) & kRingMask] = (uint8_t)s1;
           if (three) out[(at + 2u) & kRingMask] = (uint8_t)s2;
         }
+        if (STAGE) {
+          if (cnt_out + 3u <= cap_lit) {
+            op[cnt_out] = (uint8_t)s0;
+            if (two) op[cnt_out + 1] = (uint8_t)s1;
+            if (three) op[cnt_out + 2] = (uint8_t)s2;
+          } else over = true;
+        }
         cnt_out += 1u + (two ? 1u : 0u) + (three ? 1u : 0u);
-        lb.drop((int)(c0 + (two ? c1 : 0u) + (three ? c2 : 0u)));
+        lb.skip((int)(c0 + (two ? c1 : 0u) + (three ? c2 : 0u)));
       }
     }
+    lb.norm();
     if (act) {
       const uint32_t ab = lb.abit();
       if (ab > bend_abs) { flag = P_BAD; act = false; } // ran past the end of the input
@@ -440,6 +477,7 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
   p_out = (run && start < e) ? lb.abit() - lead_bits : start;
   flag_out = flag;
   n_out = cnt_out;
+  if (STAGE) *ovf = over;
 }
 
 // Replays records [0, nrec) in order, one warp.  RING: the output lives in a shared-memory ring (position modulo
