@@ -45,6 +45,10 @@ constexpr uint32_t kMinRange = 256;     // bits per lane at least
 #define FB_INF_LANE_COPY 16 // measured per GiB: 8 -> 15.3 ms, 12 -> 10.31, 16 -> 10.33, 24 -> 10.83
 #endif
 constexpr int kLaneCopyMax = FB_INF_LANE_COPY; // longest back-reference one lane copies by itself
+#ifndef FB_INF_BIG_STEP
+#define FB_INF_BIG_STEP 3 // measured per GiB, runs / mixed: old loop 4.48 / 9.59 ms, 3 -> 3.10 / 9.79, 9 -> 2.83 / 11.06
+#endif
+constexpr int kBigStep = FB_INF_BIG_STEP; // loads in flight per lane while the warp copies a long back-reference
 #ifndef FB_INF_PF
 #define FB_INF_PF 1 // lane read-ahead: 0 none, 1 into L1, 2 into L2 only
 #endif
@@ -407,13 +411,21 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
 // The same for a block whose code has no length symbols (HLIT = 257: the literal-only blocks the encoder
 // emits for incompressible data, which resynchronise poorly and therefore run many rounds): nothing but
 // literals and EOB, up to three symbols per step.
-template <bool WRITE, bool RING = false, bool STAGE = false>
+// PHASES (counting only): the start is a guess that may be off by less than `nphase` bits (nphase = the longest
+// code).  A code whose symbols nearly all have one length never falls back onto the true symbol boundaries from a
+// wrong start -- but it runs into the end-of-block symbol (the rarest one, so about once per 2^length symbols)
+// long before the range is over, which the true sequence cannot do in front of the block's last range.  So a lane
+// that meets EOB inside its range starts over one bit further on; *start_used is where the try that got through
+// (or the last one) began.
+template <bool WRITE, bool RING = false, bool STAGE = false, bool PHASES = false>
 __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t *in, int64_t cur_len, uint32_t bend,
                                                   bool run, uint32_t start, uint32_t e, uint32_t &p_out,
                                                   uint32_t &flag_out, uint32_t &n_out, uint8_t *out, uint32_t obase,
-                                                  uint32_t cap_lit = 0, bool *ovf = nullptr)
+                                                  uint32_t cap_lit = 0, bool *ovf = nullptr, uint32_t nphase = 1,
+                                                  uint32_t *start_used = nullptr)
 {
   bool over = false;
+  uint32_t phase = 0;
   const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(sm.lit);
   const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
   const uint32_t *wbase = reinterpret_cast<const uint32_t *>(in - lead);
@@ -433,8 +445,14 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
     if (act) {
       const uint32_t c0 = e0 & 15u, s0 = e0 >> 4;
       if (e0 == 0 || s0 > 256u) { flag = P_BAD; act = false; }
-      else if (s0 == 256u) { lb.skip((int)c0); flag = P_EOB; act = false; }
-      else {
+      else if (s0 == 256u) {
+        lb.skip((int)c0);
+        if (PHASES && phase + 1u < nphase && lb.abit() < e_abs) { // a wrong start: the next one
+          phase++;
+          lb.init(wbase, (uint32_t)((cur_len + lead + 3) >> 2), start + phase + lead_bits);
+          cnt_out = 0;
+        } else { flag = P_EOB; act = false; }
+      } else {
         // second symbol from the same 32-bit peek, if the first one leaves the lane inside its range and the
         // second is a literal of the direct table (anything else waits for the next step)
         const uint32_t e1 = lds_u16(lit_sa + (((bits >> c0) & ((1u << kLB) - 1u)) << 1));
@@ -478,6 +496,7 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
   flag_out = flag;
   n_out = cnt_out;
   if (STAGE) *ovf = over;
+  if (PHASES) *start_used = start + phase;
 }
 
 // Replays records [0, nrec) in order, one warp.  RING: the output lives in a shared-memory ring (position modulo
@@ -514,15 +533,37 @@ __device__ void replay_records(uint8_t *buf, const uint2 *rec, uint32_t nrec, in
         const uint32_t lenp = __shfl_sync(kFull, len, p);
         const uint32_t dd = __shfl_sync(kFull, dist, p);
         const int64_t sp = (int64_t)dstp - (int64_t)dd;
-        if (dd >= 32u) {
-          // pieces of at most dd bytes never read what they write; 32 bytes per step inside a piece
-          for (uint32_t b0 = 0; b0 < lenp; b0 += dd) {
-            const uint32_t b1 = b0 + dd < lenp ? b0 + dd : lenp;
-            for (uint32_t i = b0 + lane; i < b1; i += 32) st(dstp + i, ld(sp + i));
-            __syncwarp();
+        // Byte i of the copy is source byte i mod dd (the reference copies forward byte by byte, so a distance
+        // shorter than the length repeats the pattern: dict-decoder.mbt:136-149), and all of those lie in front of
+        // the destination: no dependencies inside the record.  kBigStep * 32 bytes per step with the loads first:
+        // a 258-byte record costs three trips to memory instead of nine.
+        if (lenp <= 32u) {
+          if ((uint32_t)lane < lenp) st(dstp + lane, ld(sp + (dd >= lenp ? (uint32_t)lane : (uint32_t)lane % dd)));
+        } else if (dd >= lenp) {
+          for (uint32_t b0 = lane; b0 < lenp; b0 += 32u * kBigStep) {
+            uint8_t v[kBigStep];
+#pragma unroll
+            for (int k = 0; k < kBigStep; k++)
+              if (b0 + 32u * k < lenp) v[k] = ld(sp + b0 + 32u * k);
+#pragma unroll
+            for (int k = 0; k < kBigStep; k++)
+              if (b0 + 32u * k < lenp) st(dstp + b0 + 32u * k, v[k]);
           }
-        } else { // overlapping: the pattern of dd bytes repeats (dict-decoder.mbt:136-149)
-          for (uint32_t i = lane; i < lenp; i += 32) st(dstp + i, ld(sp + (i % dd)));
+        } else {
+          uint32_t idx = dd > 31u ? (uint32_t)lane : (uint32_t)lane % dd;
+          const uint32_t r32 = dd > 32u ? 32u : 32u % dd;
+          for (uint32_t b0 = lane; b0 < lenp; b0 += 32u * kBigStep) {
+            uint8_t v[kBigStep];
+#pragma unroll
+            for (int k = 0; k < kBigStep; k++) {
+              if (b0 + 32u * k < lenp) v[k] = ld(sp + idx);
+              idx += r32;
+              if (idx >= dd) idx -= dd;
+            }
+#pragma unroll
+            for (int k = 0; k < kBigStep; k++)
+              if (b0 + 32u * k < lenp) st(dstp + b0 + 32u * k, v[k]);
+          }
         }
         pending &= ~(1u << p);
         __syncwarp();
@@ -739,7 +780,13 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
         bool need = true;
         for (int round = 0; round < 34; round++) {
           uint32_t tp, tf, to, tr = 0;
-          if (lit_only) decode_ranges_lit<false>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u);
+          if (lit_only && flat_code) {
+            // (round 0 starts every lane but the first at a guess: try the other phases too)
+            uint32_t su = start;
+            decode_ranges_lit<false, false, false, true>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u, 0u,
+                                                         nullptr, (round == 0 && lane > 0) ? (uint32_t)mx1 : 1u, &su);
+            if (need) start = su;
+          } else if (lit_only) decode_ranges_lit<false>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u);
           else decode_ranges<false>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, need, start, e_i, tp, tf, to, tr,
                                     nullptr, 0u, nullptr);
           if (need) { p = tp; flag = tf; n_out = to; n_rec = tr; }
