@@ -110,6 +110,7 @@ __device__ bool warp_canon(const uint8_t *lens, int nsym, uint16_t *sorted, Tab 
   }
   if (code_at_max != (1 << mx) && !(code_at_max == 1 && mx == 1)) return false; // :161
   if (lane < 16) {
+    if (lane == 0) my_first = mx; // first[0] is not a code length's entry: it keeps the longest length in use
     tab->first[lane] = (uint16_t)my_first;
     tab->count[lane] = (uint16_t)c;
     tab->offs[lane] = (uint16_t)my_off;
@@ -241,6 +242,20 @@ struct LBits {
 #endif
     }
   }
+  __device__ __forceinline__ void norm1() // after at most 32 skipped bits (bo < 64)
+  {
+    if (bo >= 32) {
+      lo = hi; hi = nx;
+      wi++;
+      nx = ld(wi + 2);
+      bo -= 32;
+#if FB_INF_PF == 2
+      if ((wi & 7u) == 0u && wi + kPrefetchWords < nwords) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + wi + kPrefetchWords));
+#elif FB_INF_PF == 1
+      if ((wi & 7u) == 0u && wi + kPrefetchWords < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + wi + kPrefetchWords));
+#endif
+    }
+  }
   __device__ __forceinline__ uint32_t abit() const { return (wi << 5) + (uint32_t)bo; }
 };
 
@@ -296,6 +311,8 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
   LBits lb;
   lb.init(wbase, (uint32_t)((cur_len + lead + 3) >> 2), (run ? start : 0u) + lead_bits);
   const uint32_t e_abs = e + lead_bits, bend_abs = bend + lead_bits;
+  const uint32_t lim_abs = e_abs < bend_abs + 1u ? e_abs : bend_abs + 1u; // a further symbol may start below this
+  const bool long_lit = sm.tl.first[0] > (uint32_t)kLB, long_dist = sm.td.first[0] > (uint32_t)kDB; // codes beyond the direct tables?
   uint32_t flag = P_OK, cnt_out = 0, cnt_rec = 0;
   uint8_t *op = out + obase;
   bool act = run && start < e;
@@ -308,7 +325,7 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
 #endif
     const uint32_t bits = lb.peek();
     uint32_t e0 = lds_u16(lit_sa + ((bits & ((1u << kLB) - 1u)) << 1));
-    if (__any_sync(kFull, act && e0 == 0)) {
+    if (long_lit && __any_sync(kFull, act && e0 == 0)) {
       if (act && e0 == 0) e0 = canon_long(bits, kLB + 1, &sm.tl, sm.lsorted);
     }
     const uint32_t cl = e0 & 15u, sym = e0 >> 4;
@@ -330,12 +347,12 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
         const uint32_t e1 = lds_u16(lit_sa + (((bits >> cl) & ((1u << kLB) - 1u)) << 1));
         const uint32_t c1 = e1 & 15u, s1 = e1 >> 4;
         const uint32_t ab0 = lb.abit() + cl;
-        const bool two = e1 != 0 && s1 < 256u && ab0 < e_abs && ab0 <= bend_abs;
+        const bool two = e1 != 0 && s1 < 256u && ab0 < lim_abs;
         const uint32_t e2 = lds_u16(lit_sa + (((bits >> (cl + c1)) & ((1u << kLB) - 1u)) << 1));
         const uint32_t c2 = e2 & 15u, s2 = e2 >> 4;
         const uint32_t ab1 = ab0 + c1;
         // (the third look-up needs its 10 index bits inside the 32-bit peek: cl + c1 <= 22)
-        const bool three = two && cl + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
+        const bool three = two && cl + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < lim_abs;
         if (WRITE && !RING) {
           op[cnt_out] = (uint8_t)sym;
           if (two) op[cnt_out + 1] = (uint8_t)s1;
@@ -365,7 +382,7 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
       if (is_len && act) {
         const uint32_t dbits = lb.peek_at(lb.bo);
         uint32_t d = lds_u16(dist_sa + ((dbits & ((1u << kDB) - 1u)) << 1));
-        if (d == 0) d = canon_long(dbits, kDB + 1, &sm.td, sm.dsorted);
+        if (long_dist && d == 0) d = canon_long(dbits, kDB + 1, &sm.td, sm.dsorted);
         if (d == 0 || (d >> 4) >= (uint32_t)kNumDist) { flag = P_BAD; act = false; }
         else {
           const uint32_t dl = d & 15u;
@@ -433,13 +450,15 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
   LBits lb;
   lb.init(wbase, (uint32_t)((cur_len + lead + 3) >> 2), (run ? start : 0u) + lead_bits);
   const uint32_t e_abs = e + lead_bits, bend_abs = bend + lead_bits;
+  const uint32_t lim_abs = e_abs < bend_abs + 1u ? e_abs : bend_abs + 1u; // a further symbol may start below this
+  const bool long_lit = sm.tl.first[0] > (uint32_t)kLB; // codes beyond the direct table?
   uint32_t flag = P_OK, cnt_out = 0;
   uint8_t *op = out + obase;
   bool act = run && start < e;
   while (__any_sync(kFull, act)) {
     const uint32_t bits = lb.peek();
     uint32_t e0 = lds_u16(lit_sa + ((bits & ((1u << kLB) - 1u)) << 1));
-    if (__any_sync(kFull, act && e0 == 0)) {
+    if (long_lit && __any_sync(kFull, act && e0 == 0)) {
       if (act && e0 == 0) e0 = canon_long(bits, kLB + 1, &sm.tl, sm.lsorted);
     }
     if (act) {
@@ -458,11 +477,11 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
         const uint32_t e1 = lds_u16(lit_sa + (((bits >> c0) & ((1u << kLB) - 1u)) << 1));
         const uint32_t c1 = e1 & 15u, s1 = e1 >> 4;
         const uint32_t ab0 = lb.abit() + c0;
-        const bool two = e1 != 0 && s1 < 256u && ab0 < e_abs && ab0 <= bend_abs;
+        const bool two = e1 != 0 && s1 < 256u && ab0 < lim_abs;
         const uint32_t e2 = lds_u16(lit_sa + (((bits >> (c0 + c1)) & ((1u << kLB) - 1u)) << 1));
         const uint32_t c2 = e2 & 15u, s2 = e2 >> 4;
         const uint32_t ab1 = ab0 + c1;
-        const bool three = two && c0 + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < e_abs && ab1 <= bend_abs;
+        const bool three = two && c0 + c1 + (uint32_t)kLB <= 32u && e2 != 0 && s2 < 256u && ab1 < lim_abs;
         if (WRITE && !RING) {
           op[cnt_out] = (uint8_t)s0;
           if (two) op[cnt_out + 1] = (uint8_t)s1;
@@ -485,7 +504,7 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
         lb.skip((int)(c0 + (two ? c1 : 0u) + (three ? c2 : 0u)));
       }
     }
-    lb.norm();
+    lb.norm1();
     if (act) {
       const uint32_t ab = lb.abit();
       if (ab > bend_abs) { flag = P_BAD; act = false; } // ran past the end of the input

@@ -21,6 +21,19 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
+def kernel_source_hash():
+    """the same hash bench.py computes: sha256 over moonbit_flate_b200/csrc/*.{cu,cuh,h} of the tree the capture was made from"""
+    import hashlib, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "moonbit_flate_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def launches(src, dst, cmd):
     rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("==")) if r]
     hdr = rows[0]
@@ -71,7 +84,8 @@ def full(src, dst, traffic=None):
                 "inflate" if "k_inflate_par" in d["Kernel Name"] else None)
             if name:
                 t[name] = int(gb(d, "dram__bytes_read.sum") + gb(d, "dram__bytes_write.sum"))
-        t["source"] = f"ncu --set full ({dst}): dram__bytes_read.sum + dram__bytes_write.sum per launch, 16384 x 64 KiB mixed segments"
+        t["capture"] = f"ncu --set full ({dst}): dram__bytes_read.sum + dram__bytes_write.sum per launch, 16384 x 64 KiB mixed segments"
+        t["kernel_source_sha256_16"] = kernel_source_hash()
         json.dump(t, open(traffic, "w"), indent=1)
         print(t)
 
