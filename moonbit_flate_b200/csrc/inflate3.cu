@@ -556,9 +556,10 @@ __device__ void replay_records(uint8_t *buf, const uint2 *rec, uint32_t nrec, in
         // shorter than the length repeats the pattern: dict-decoder.mbt:136-149), and all of those lie in front of
         // the destination: no dependencies inside the record.  kBigStep * 32 bytes per step with the loads first:
         // a 258-byte record costs three trips to memory instead of nine.
-        if (lenp <= 32u) {
-          if ((uint32_t)lane < lenp) st(dstp + lane, ld(sp + (dd >= lenp ? (uint32_t)lane : (uint32_t)lane % dd)));
-        } else if (dd >= lenp) {
+        if (dd >= lenp) { // (the usual case: source and destination do not overlap)
+          if (lenp <= 32u) {
+            if ((uint32_t)lane < lenp) st(dstp + lane, ld(sp + lane));
+          } else
           for (uint32_t b0 = lane; b0 < lenp; b0 += 32u * kBigStep) {
             uint8_t v[kBigStep];
 #pragma unroll
