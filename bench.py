@@ -683,6 +683,10 @@ def main():
             "compression_ratio": round(float(sums[0].item()) / total_unc, 5),
             "parity": f"round trip bit-exact on every stream; {n_checked} streams byte-identical to the oracle",
             "roofline": roofline, "clocks": clocks, "gpu_launches": launches[0]}
+    if world > 1:
+        # what a step spends outside the kernels: size all-gather, peer copies into GPU 0's frame, header, peer copies
+        # back out of it (all ranks' streams pass through one GPU's NVLink ports, once in each direction)
+        line["frame_exchange_ms_per_step"] = round(ms_step - sum(st_ms.values()), 3)
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
