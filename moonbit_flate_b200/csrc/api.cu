@@ -274,12 +274,6 @@ extern "C" int fb200_create(fb200_ctx **out, int device)
     return FB200_ERR_CUDA;
   }
   ctx->num_sms = prop.multiProcessorCount;
-  if (const char *e = getenv("FB200_L2_FETCH")) { // experiment: maximum L2 fetch granularity in bytes (32 / 64 / 128)
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
-    size_t got = 0;
-    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-    fprintf(stderr, "[fb200] L2 fetch granularity: %zu\n", got);
-  }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost((void **)&ctx->pinned, 64 * sizeof(uint64_t)) != cudaSuccess ||
       cudaMallocHost((void **)&ctx->h_gbounds, 2 * (fb200_ctx::kMaxGroups + 1) * sizeof(uint64_t)) != cudaSuccess) {
