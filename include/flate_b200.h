@@ -265,9 +265,12 @@ int fb200_debug_block_resets(uint64_t b);
  *   FB200_DEFLATE_PIPELINE=0  host-buffer deflate: K2..K4 in one piece instead of group by group
  *   FB200_PARSE_BLOCKPAR=0|1|2  block-parallel parse of multi-block streams: never / when few streams / always
  *   FB200_PARSE_WARPS=s, FB200_PARSE_GWARPS=g  parse warps per SM with shared-memory / global-memory tables
+ *   FB200_PARSE_CARVEOUT=p    shared-memory carve-out hint (percent) of the parse kernels; default: the smallest
+ *                             one that holds the tables
  *   FB200_INFLATE_CTAS=c      inflate CTAs (4 warps each) per SM
+ *   FB200_INFLATE_WINDOW_KB=k speculation window of a stream's first block (96; 0: the whole rest of the stream)
  *   FB200_INFLATE_CTA_STREAMS=n  calls with at most n streams inflate with one CTA per stream (296; 0: never)
- *   FB200_TRACE=1             timeline of the host-buffer calls on stderr */
+ *   FB200_TRACE=1|2           inflate round / block counters (1), timeline of the host-buffer calls (2) on stderr */
 
 #ifdef __cplusplus
 }
