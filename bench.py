@@ -12,7 +12,10 @@ the 8-GPU run is the 8 GiB corpus of configs[3]; --scaling strong splits a
 fixed 8 GiB corpus over the ranks instead).  One step = one deflate pass over
 the rank's shard, at N > 1 the all-gather of segment sizes and the frame
 assembly on GPU 0 over NVLink followed by the fetch of the rank's range back
-out of the frame, and one inflate pass over those streams.  value =
+out of the frame, and one inflate pass over those streams (at N > 1 the K
+steps are software-pipelined: every batch still takes all of these stages, but
+its way back out of the frame travels beside the deflate of the next batch and
+the next batch's way in beside its inflate -- copy engines next to kernels).  value =
 uncompressed bytes through the codec per second = 2 * N_uncompressed / t_step,
 inputs resident in HBM.  The other BASELINE configs are selected with
 --workload (small = configs[2], random / runs = configs[4]); the default N=1
@@ -444,7 +447,8 @@ def main():
         d_fcomp = torch.zeros(dc.cap, dtype=torch.uint8, device=dev)
         d_fcoff = torch.zeros(nunits + 1, dtype=torch.int64, device=dev)
         config["frame"] = ("assembled on GPU 0 with cuda-ipc peer copies (copy engines over NVLink) and read back by every rank "
-                           "with fb200_mg_get before its inflate pass" if peer else
+                           "with fb200_mg_get_async before its inflate pass; steps software-pipelined: the way back of batch i "
+                           "beside the deflate of batch i + 1, the way in of batch i + 1 beside the inflate of batch i" if peer else
                            "assembled on GPU 0 and scattered back with nccl send/recv before the inflate pass")
 
     stage_acc = {}
@@ -475,14 +479,50 @@ def main():
             launches[0] += int(ctx.last_stats().kernel_launches)
             stage_acc["inflate"] = stage_acc.get("inflate", 0.0) + ctx.last_stage_ms()["inflate"]
 
+    def run_steps(k, record):
+        """k steps.  With the frame on GPU 0 (N > 1, peer copies) the steps are software-pipelined: every batch is
+        still deflated, put into the frame, read back out of it and inflated, but the way back of batch i travels
+        beside the deflate of batch i + 1 and the way in of batch i + 1 beside the inflate of batch i (copy engines
+        over NVLink next to the kernels), instead of all ranks pushing and then all ranks pulling through GPU 0's
+        ports while the SMs wait.  (Before anyone puts batch i + 1, every rank has its batch i back: the size
+        all-gather inside put comes after the rank's mg_wait.)"""
+        if not (world > 1 and peer):
+            for _ in range(k):
+                step(record)
+            return
+
+        def deflate_rec():
+            dc.deflate()
+            if record:
+                launches[0] += int(ctx.last_stats().kernel_launches)
+                for kk, v in ctx.last_stage_ms().items():
+                    stage_acc[kk] = stage_acc.get(kk, 0.0) + v
+
+        def put():
+            frame_len[0] = peer.put(dc.d_dst, dc.d_doff[1:] - dc.d_doff[:-1], seg or 0, nseg_total=units_total)
+
+        deflate_rec()
+        put()
+        for i in range(k):
+            peer.wait()  # this rank's payload and the header of batch i are in GPU 0's frame
+            peer.get_begin(first, nunits, d_fcomp, d_fcoff)
+            if i + 1 < k:
+                deflate_rec()  # batch i + 1, beside the way back of batch i
+            ctx.mg_wait()  # batch i has arrived
+            if i + 1 < k:
+                put()  # batch i + 1 on its way in, beside the inflate below
+            dc.inflate(d_fcomp, d_fcoff)
+            if record:
+                launches[0] += int(ctx.last_stats().kernel_launches)
+                stage_acc["inflate"] = stage_acc.get("inflate", 0.0) + ctx.last_stage_ms()["inflate"]
+
     # warm-up (untimed) + parity check of the resident result
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(args.warmup):
-        step(record=False)
+    run_steps(args.warmup, record=False)
     torch.cuda.synchronize()
     dc.d_out.zero_()
-    step(record=False)  # same load right before the timed region (also keeps the clocks up for the sampler)
+    run_steps(1, record=False)  # same load right before the timed region (also keeps the clocks up for the sampler)
     torch.cuda.synchronize()
     if peer:
         peer.wait_all()
@@ -508,8 +548,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
     e0.record(lib_stream)
-    for _ in range(args.steps):
-        step(record=True)
+    run_steps(args.steps, record=True)
     torch.cuda.synchronize()
     e1.record(lib_stream)
     e1.synchronize()

@@ -159,7 +159,7 @@ int fb200_mg_frame_close(fb200_ctx *ctx, void *d_frame, int owner);
 /* Asynchronous copy of n bytes from d_payload (this context's GPU) to d_frame + offset
  * (local or IPC-mapped), ordered after everything queued so far on the context stream. */
 int fb200_mg_put(fb200_ctx *ctx, void *d_frame, uint64_t offset, const void *d_payload, uint64_t n);
-/* Blocks until every fb200_mg_put of this context has landed. */
+/* Blocks until every fb200_mg_put / fb200_mg_get_async of this context has landed. */
 int fb200_mg_wait(fb200_ctx *ctx);
 /* Frame reader (decompress side, SURVEY.md 8e: "scatter compressed ranges, decode locally"): fetches the
  * compressed streams of segments [first, first + count) from a frame of frame_bytes bytes at d_frame -- on this
@@ -170,6 +170,12 @@ int fb200_mg_wait(fb200_ctx *ctx);
 int fb200_mg_get(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint64_t first, uint64_t count,
                  uint8_t *d_comp, uint64_t comp_cap, uint64_t *d_comp_off, uint32_t *seg_size, uint64_t *nseg_total,
                  uint64_t *out_bytes);
+/* The same, but returns once the offsets are in d_comp_off and the payload copy is queued (the header fields and
+ * *out_bytes are final on return); fb200_mg_wait blocks until the payload has arrived.  Lets the caller run other
+ * work of the same context (the deflate of the next batch) beside the transfer. */
+int fb200_mg_get_async(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint64_t first, uint64_t count,
+                       uint8_t *d_comp, uint64_t comp_cap, uint64_t *d_comp_off, uint32_t *seg_size,
+                       uint64_t *nseg_total, uint64_t *out_bytes);
 
 /* ------------------------------------------------------------------ */
 /* Streaming objects mirroring the reference API (host buffers).       */

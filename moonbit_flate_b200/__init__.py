@@ -89,6 +89,8 @@ ABI = {
     "fb200_mg_wait": (C.c_int, [C.c_void_p]),
     "fb200_mg_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, C.c_uint64, _u64p,
                                C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fb200_mg_get_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, C.c_uint64, _u64p,
+                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fb200_writer_new": (C.c_void_p, [C.c_void_p, SINK_FN, C.c_void_p]),
     "fb200_writer_new_dict": (C.c_void_p, [C.c_void_p, SINK_FN, C.c_void_p, _u8p, C.c_uint64]),
     "fb200_writer_write": (C.c_int64, [C.c_void_p, _u8p, C.c_uint64]),
@@ -311,6 +313,14 @@ class Context:
         seg, nseg, nb = C.c_uint32(), C.c_uint64(), C.c_uint64()
         self._check(_lib.fb200_mg_get(self._h, d_frame, frame_bytes, first, count, d_comp, comp_cap, d_comp_off,
                                       C.byref(seg), C.byref(nseg), C.byref(nb)), "fb200_mg_get")
+        return int(seg.value), int(nseg.value), int(nb.value)
+
+    def mg_get_async(self, d_frame: int, frame_bytes: int, first: int, count: int, d_comp: int, comp_cap: int, d_comp_off: int):
+        """mg_get without the final wait: the payload is on its way when this returns, ``mg_wait`` blocks until it
+        has arrived -> (seg_size, nseg_total, bytes)."""
+        seg, nseg, nb = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._check(_lib.fb200_mg_get_async(self._h, d_frame, frame_bytes, first, count, d_comp, comp_cap, d_comp_off,
+                                      C.byref(seg), C.byref(nseg), C.byref(nb)), "fb200_mg_get_async")
         return int(seg.value), int(nseg.value), int(nb.value)
 
     def last_blocks(self, nblocks: int, tok_cap: int):

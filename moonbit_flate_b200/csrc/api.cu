@@ -466,9 +466,9 @@ extern "C" int fb200_mg_wait(fb200_ctx *ctx)
 // the assembling GPU and mapped through CUDA IPC: a peer copy over NVLink) into d_comp, and their offsets
 // (count + 1 values, starting at 0) are written to d_comp_off.  The sizes are read from the frame header by a
 // kernel (peer loads when the frame is remote); the payload moves with the copy engines.
-extern "C" int fb200_mg_get(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint64_t first, uint64_t count,
-                            uint8_t *d_comp, uint64_t comp_cap, uint64_t *d_comp_off, uint32_t *seg_size, uint64_t *nseg_total,
-                            uint64_t *out_bytes)
+static int mg_get_impl(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint64_t first, uint64_t count,
+                       uint8_t *d_comp, uint64_t comp_cap, uint64_t *d_comp_off, uint32_t *seg_size, uint64_t *nseg_total,
+                       uint64_t *out_bytes, bool wait)
 {
   if (!ctx || !d_frame || !d_comp_off || (!d_comp && comp_cap) || !out_bytes) return FB200_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -497,8 +497,24 @@ extern "C" int fb200_mg_get(fb200_ctx *ctx, const void *d_frame, uint64_t frame_
   if (base + total > frame_bytes) { ctx->err = "frame truncated: the streams of the range end beyond it"; return FB200_ERR_ARG; }
   if (total > comp_cap) { ctx->err = "comp_cap too small"; return FB200_ERR_DST_TOO_SMALL; }
   if (total) CK(cudaMemcpyAsync(d_comp, static_cast<const uint8_t *>(d_frame) + base, total, cudaMemcpyDefault, st));
-  CK(cudaStreamSynchronize(st));
+  if (wait) CK(cudaStreamSynchronize(st));
   return FB200_OK;
+}
+
+extern "C" int fb200_mg_get(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint64_t first, uint64_t count,
+                            uint8_t *d_comp, uint64_t comp_cap, uint64_t *d_comp_off, uint32_t *seg_size, uint64_t *nseg_total,
+                            uint64_t *out_bytes)
+{
+  return mg_get_impl(ctx, d_frame, frame_bytes, first, count, d_comp, comp_cap, d_comp_off, seg_size, nseg_total, out_bytes,
+                     true);
+}
+
+extern "C" int fb200_mg_get_async(fb200_ctx *ctx, const void *d_frame, uint64_t frame_bytes, uint64_t first, uint64_t count,
+                                  uint8_t *d_comp, uint64_t comp_cap, uint64_t *d_comp_off, uint32_t *seg_size,
+                                  uint64_t *nseg_total, uint64_t *out_bytes)
+{
+  return mg_get_impl(ctx, d_frame, frame_bytes, first, count, d_comp, comp_cap, d_comp_off, seg_size, nseg_total, out_bytes,
+                     false);
 }
 
 // ------------------------------------------------------------------

@@ -228,6 +228,13 @@ class PeerFrame:
         return self.ctx.mg_get(self.ptr, self.length, first, count, d_comp.data_ptr(), int(d_comp.numel()),
                                d_comp_off.data_ptr())
 
+    def get_begin(self, first: int, count: int, d_comp: torch.Tensor, d_comp_off: torch.Tensor):
+        """``get`` without the final wait: the offsets are in d_comp_off and the payload is on its way when this
+        returns; ``ctx.mg_wait()`` blocks until it has arrived.  Whatever the caller runs in between (the deflate of
+        its next batch) overlaps the transfer."""
+        return self.ctx.mg_get_async(self.ptr, self.length, first, count, d_comp.data_ptr(), int(d_comp.numel()),
+                                     d_comp_off.data_ptr())
+
     def wait(self):
         """This rank's payload has landed in the frame and the header (written by rank 0) is complete: everything
         this rank reads back with ``get`` is there.  No barrier: a rank does not wait for the payloads of the others,

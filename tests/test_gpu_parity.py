@@ -472,6 +472,14 @@ def test_peer_frame_single_rank(ctx, corpus):
                                   d_olen.data_ptr(), d_st.data_ptr(), d_eo.data_ptr())
             assert int(d_st.abs().sum()) == 0
             assert np.array_equal(d_out.cpu().numpy(), src[first * seg: (first + count) * seg])
+    # the asynchronous form: offsets and sizes are final on return, the payload after mg_wait
+    d_comp = torch.zeros(comp.size + 16, dtype=torch.uint8, device=dev)
+    d_coff = torch.zeros(31, dtype=torch.int64, device=dev)
+    seg_size, n, nbytes = pf.get_begin(7, 30, d_comp, d_coff)
+    assert (seg_size, n) == (seg, nseg) and nbytes == int(off[37] - off[7])
+    ctx.mg_wait()
+    assert np.array_equal(d_coff.cpu().numpy().astype(np.uint64), off[7:38] - off[7])
+    assert np.array_equal(d_comp[:nbytes].cpu().numpy(), comp[int(off[7]): int(off[37])])
     import moonbit_flate_b200 as fb
     with pytest.raises(fb.FlateError):
         pf.get(nseg - 1, 2, torch.zeros(16, dtype=torch.uint8, device=dev), torch.zeros(3, dtype=torch.int64, device=dev))
