@@ -288,19 +288,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
 constexpr uint32_t kRing = 128u * 1024u;
 constexpr uint32_t kRingMask = kRing - 1u;
 
-// STAGE (with WRITE = false): a counting pass that also keeps what it decodes -- literals at out[position
-// relative to the lane's start] (the lane's slot of cap_lit bytes), back-references in rec[] (the lane's slot of
-// cap_rec records) with relative destinations; a lane whose slot is too small goes on counting and says so in
-// *ovf.  When no lane overflowed the block is finished by copying the slots into place, without a second decode.
-template <bool WRITE, bool RING = false, bool STAGE = false>
+template <bool WRITE, bool RING = false>
 __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_len_tab, const uint32_t *s_dist_tab,
                                               const uint8_t *in, int64_t cur_len, uint32_t bend, bool run,
                                               uint32_t start, uint32_t e, uint32_t &p_out, uint32_t &flag_out,
                                               uint32_t &n_out, uint32_t &n_rec, uint8_t *out, uint32_t obase,
-                                              uint2 *rec, uint32_t h0 = 0, uint32_t cap_lit = 0, uint32_t cap_rec = 0,
-                                              bool *ovf = nullptr)
+                                              uint2 *rec, uint32_t h0 = 0)
 {
-  bool over = false;
   const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(sm.lit);
   const uint32_t dist_sa = (uint32_t)__cvta_generic_to_shared(sm.dist);
   const uint32_t ltab_sa = (uint32_t)__cvta_generic_to_shared(s_len_tab);
@@ -364,13 +358,6 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
           if (two) out[(at + 1u) & kRingMask] = (uint8_t)s1;
           if (three) out[(at + 2u) & kRingMask] = (uint8_t)s2;
         }
-        if (STAGE) {
-          if (cnt_out + 3u <= cap_lit) {
-            op[cnt_out] = (uint8_t)sym;
-            if (two) op[cnt_out + 1] = (uint8_t)s1;
-            if (three) op[cnt_out + 2] = (uint8_t)s2;
-          } else over = true;
-        }
         cnt_out += 1u + (two ? 1u : 0u) + (three ? 1u : 0u);
         lb.skip((int)(cl + (two ? c1 : 0u) + (three ? c2 : 0u)));
       } else {
@@ -395,11 +382,6 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
             if (dist > at + h0) { flag = P_BAD; act = false; } // dist > hist_size (inflate.mbt:677), h0 = dictionary
             else rec[cnt_rec] = make_uint2(at, length | ((dist - 1u) << 16));
           }
-          if (STAGE) { // (dist > hist_size is checked when the records are moved into place)
-            const uint32_t dist = (dt & 0xffffu) + ((dbits >> dl) & ((1u << dxb) - 1u));
-            if (cnt_rec < cap_rec) rec[cnt_rec] = make_uint2(cnt_out, length | ((dist - 1u) << 16));
-            else over = true;
-          }
           cnt_out += length;
           cnt_rec++;
         }
@@ -422,7 +404,6 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
   flag_out = flag;
   n_out = cnt_out;
   n_rec = cnt_rec;
-  if (STAGE) *ovf = over;
 }
 
 // The same for a block whose code has no length symbols (HLIT = 257: the literal-only blocks the encoder
@@ -434,14 +415,12 @@ __device__ __forceinline__ void decode_ranges(const Smem &sm, const uint32_t *s_
 // long before the range is over, which the true sequence cannot do in front of the block's last range.  So a lane
 // that meets EOB inside its range starts over one bit further on; *start_used is where the try that got through
 // (or the last one) began.
-template <bool WRITE, bool RING = false, bool STAGE = false, bool PHASES = false>
+template <bool WRITE, bool RING = false, bool PHASES = false>
 __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t *in, int64_t cur_len, uint32_t bend,
                                                   bool run, uint32_t start, uint32_t e, uint32_t &p_out,
                                                   uint32_t &flag_out, uint32_t &n_out, uint8_t *out, uint32_t obase,
-                                                  uint32_t cap_lit = 0, bool *ovf = nullptr, uint32_t nphase = 1,
-                                                  uint32_t *start_used = nullptr)
+                                                  uint32_t nphase = 1, uint32_t *start_used = nullptr)
 {
-  bool over = false;
   uint32_t phase = 0;
   const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(sm.lit);
   const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
@@ -493,13 +472,6 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
           if (two) out[(at + 1u) & kRingMask] = (uint8_t)s1;
           if (three) out[(at + 2u) & kRingMask] = (uint8_t)s2;
         }
-        if (STAGE) {
-          if (cnt_out + 3u <= cap_lit) {
-            op[cnt_out] = (uint8_t)s0;
-            if (two) op[cnt_out + 1] = (uint8_t)s1;
-            if (three) op[cnt_out + 2] = (uint8_t)s2;
-          } else over = true;
-        }
         cnt_out += 1u + (two ? 1u : 0u) + (three ? 1u : 0u);
         lb.skip((int)(c0 + (two ? c1 : 0u) + (three ? c2 : 0u)));
       }
@@ -514,7 +486,6 @@ __device__ __forceinline__ void decode_ranges_lit(const Smem &sm, const uint8_t 
   p_out = (run && start < e) ? lb.abit() - lead_bits : start;
   flag_out = flag;
   n_out = cnt_out;
-  if (STAGE) *ovf = over;
   if (PHASES) *start_used = start + phase;
 }
 
@@ -589,11 +560,10 @@ __device__ void replay_records(uint8_t *buf, const uint2 *rec, uint32_t nrec, in
         __syncwarp();
         continue;
       }
-      // parallel round: every pending small record whose source lies before the first unresolved destination,
-      // up to the first pending big record (records after it may depend on it)
+      // parallel round: every pending small record whose source lies before the first unresolved destination (it
+      // reads nothing a pending record -- small or big -- still has to write)
       const bool mine = ((pending >> lane) & 1u) && !big && (lane == p || src_end <= dstp);
-      const unsigned bigm = __ballot_sync(kFull, big) & pending;
-      const unsigned ready = __ballot_sync(kFull, mine) & (bigm ? ((1u << (__ffs(bigm) - 1)) - 1u) : kFull);
+      const unsigned ready = __ballot_sync(kFull, mine);
       if ((ready >> lane) & 1u) {
         if (RING) {
           uint8_t v[kLaneCopyMax];
@@ -803,8 +773,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) k_inflate_par(InflateJob j)
           if (lit_only && flat_code) {
             // (round 0 starts every lane but the first at a guess: try the other phases too)
             uint32_t su = start;
-            decode_ranges_lit<false, false, false, true>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u, 0u,
-                                                         nullptr, (round == 0 && lane > 0) ? (uint32_t)mx1 : 1u, &su);
+            decode_ranges_lit<false, false, true>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u,
+                                                  (round == 0 && lane > 0) ? (uint32_t)mx1 : 1u, &su);
             if (need) start = su;
           } else if (lit_only) decode_ranges_lit<false>(sm, in, cur_len, bend, need, start, e_i, tp, tf, to, nullptr, 0u);
           else decode_ranges<false>(sm, s_len_tab, s_dist_tab, in, cur_len, bend, need, start, e_i, tp, tf, to, tr,
