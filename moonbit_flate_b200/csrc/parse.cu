@@ -64,33 +64,31 @@ constexpr unsigned kFull = 0xffffffffu;
 #define FB_PF_DIST 32 // measured: 24 -> 18.77 ms, 32 -> 18.48, 48 -> 18.72, 64 -> 18.80
 #endif
 
-// match_len tail (deflate-fast.mbt:286-307): number of equal bytes of src[s2..] and src[t..], at most a,
-// given that the first `from` already matched.  32 bytes per step; long matches take four steps per
-// round trip to memory.
-__device__ __forceinline__ int match_tail(const uint8_t *srcb, int s2, int t, int a, int from, int lane)
+// match_len tail (deflate-fast.mbt:286-307): number of equal bytes of src[s2..] and src[t..] (t < s2), at most a,
+// given that the first `from` already matched.  128 bytes per step: lane l compares the four bytes at offset
+// off + 4 l of both sides as one word, so the longest match (258) takes two trips to memory and a match that ends
+// in the first 128 bytes one.  n = bytes in the block (words that would reach beyond it are read byte by byte).
+__device__ __forceinline__ int match_tail(const uint8_t *srcb, int s2, int t, int a, int from, int lane, int n)
 {
-  const uint8_t *ps = srcb + s2 + lane, *pt = srcb + t + lane;
-  int off = from;
-  while (off < a) {
-    if (a - off > 32) {
-      bool mism[4];
+  for (int off = from; off < a; off += 128) {
+    const int i = off + 4 * lane;
+    uint32_t x = 0;
+    if (i < a) {
+      if (s2 + i + 8 <= n) {
+        x = ld32u(srcb + s2 + i) ^ ld32u(srcb + t + i);
+        if (i + 4 > a) x &= (1u << (8 * (a - i))) - 1u;
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int i = off + 32 * k + lane;
-        mism[k] = (i >= a) || (__ldg(ps + off + 32 * k) != __ldg(pt + off + 32 * k));
+        for (int k = 0; k < 4; k++)
+          if (i + k < a) x |= (uint32_t)(__ldg(srcb + s2 + i + k) ^ __ldg(srcb + t + i + k)) << (8 * k);
       }
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const unsigned mm = __ballot_sync(kFull, mism[k]);
-        if (mm) return off + 32 * k + __ffs(mm) - 1;
-      }
-      off += 128;
-    } else {
-      const int i = off + lane;
-      const bool mism = (i >= a) || (__ldg(ps + off) != __ldg(pt + off));
-      const unsigned mm = __ballot_sync(kFull, mism);
-      if (mm) return off + __ffs(mm) - 1;
-      off += 32;
+    }
+    const unsigned mm = __ballot_sync(kFull, i >= a || x != 0);
+    if (mm) {
+      const int l = __ffs(mm) - 1;
+      const uint32_t xl = __shfl_sync(kFull, x, l);
+      const int il = off + 4 * l;
+      return xl ? il + ((__ffs(xl) - 1) >> 3) : a; // (xl == 0: lane l lies beyond the limit)
     }
   }
   return a;
@@ -290,7 +288,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
                 const int t = __shfl_sync(kFull, cand, m) + 4;
                 int s1 = s2 + kMaxMatchLength - 4;
                 if (s1 > n) s1 = n;
-                ext = match_tail(srcb, s2, t, s1 - s2, ext, lane);
+                ext = match_tail(srcb, s2, t, s1 - s2, ext, lane, n);
                 if (lane == m) my_ext = ext;
               }
               s = s2 + ext;
@@ -392,7 +390,7 @@ __device__ __forceinline__ void parse_worker(const DeflateJob &j, uint32_t *coun
         if (t >= 0) {
           int s1 = s2 + kMaxMatchLength - 4;
           if (s1 > n) s1 = n;
-          ext = match_tail(srcb, s2, t, s1 - s2, 0, lane);
+          ext = match_tail(srcb, s2, t, s1 - s2, 0, lane, n);
         }
         if (lane == 0) // match_token(l + 4 - 3, s - t - 1) (:228-233)
           __stcs(&tok[ntok], kMatchType + ((uint32_t)(ext + 1) << kLengthShift) + (uint32_t)(s2 - t - 1));
