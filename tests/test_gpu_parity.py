@@ -420,6 +420,22 @@ def test_config5_worst_cases(ctx, oracle, corpus, klass):
     assert (st == 0).all() and (olen == seg).all() and np.array_equal(out, src)
 
 
+def test_flat_codes_stay_on_the_fast_path(ctx, corpus):
+    """Incompressible streams of ragged sizes, single- and multi-block: their literal-only codes (255 symbols of 8
+    bits) give the speculative decoder nothing to synchronise on, so it searches the start phase of every range (a
+    wrong phase runs into EOB early).  The result must be exact AND come from the fast kernel: a wrong guess that
+    survived would be caught by its consistency checks and handed to the exact kernel, which this test forbids."""
+    rng = np.random.default_rng(77)
+    sizes = [1000, 4096, 65535, 65536, 65537, 100000, 131070, 200000, 262144, 300001] + [int(x) for x in rng.integers(2000, 150000, 90)]
+    parts = [corpus.unit(n, seed=78, index=i, klass=2) for i, n in enumerate(sizes)]
+    src = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    comp, doff = ctx.deflate_streams(src, off)
+    out, olen, st, eo, cons = ctx.inflate_batch(comp, doff, off)
+    assert (st == 0).all() and np.array_equal(olen, np.diff(off)) and np.array_equal(out, src)
+    assert int(ctx.last_stats().inflate_fallbacks) == 0
+
+
 def test_fuzz_deflate_inflate_against_oracle(ctx, oracle):
     rng = np.random.default_rng(20260101)
     datas = fuzz_streams(rng, 420)
