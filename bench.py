@@ -486,6 +486,8 @@ def main():
         over NVLink next to the kernels), instead of all ranks pushing and then all ranks pulling through GPU 0's
         ports while the SMs wait.  (Before anyone puts batch i + 1, every rank has its batch i back: the size
         all-gather inside put comes after the rank's mg_wait.)"""
+        if k <= 0:
+            return
         if not (world > 1 and peer):
             for _ in range(k):
                 step(record)
